@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- BigVGAN decode audio-seconds/second on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one decode of 32 utterances x 10 s (T0 = 235 latent frames, 281-frame reference mel) per
+GPU in bf16 (BASELINE config 3; at N = 8 this is config 4: 256 utterances sharded by utterance,
+32 per GPU) followed, for N > 1, by one NCCL all_gather of the waveforms.  Weak scaling.
+Prints ONE JSON line on rank 0.  `--impl reference` times the reference's CPU algorithm (the
+oracle port, torch fp32 on all host threads) on a bounded sample of the same workload."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T0 = 235                    # "10 s": 240 640 samples = 10.027 s at 24 kHz
+TM = 281                    # 3 s reference mel (hop 256 @ 24 kHz)
+B_PER_GPU = 32
+SR = 24000
+UP = 1024
+AUDIO_S_PER_UTT = T0 * UP / SR
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def algorithmic_work(h, B, T0_):
+    """FLOPs of all dense convs and Activation1d bytes (2*B*C*T*sizeof) per step."""
+    C0 = h.upsample_initial_channel
+    conv_mac = C0 * h.gpt_dim * 7 * T0_
+    convtr_mac = 0
+    act_elems = 0
+    T = T0_
+    for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+        cin, cout = C0 >> i, C0 >> (i + 1)
+        convtr_mac += cin * cout * k * T
+        T *= u
+        for rk in h.resblock_kernel_sizes:
+            conv_mac += 6 * cout * cout * rk * T
+            act_elems += 6 * cout * T
+    cp = C0 >> len(h.upsample_rates)
+    act_elems += cp * T
+    post_mac = cp * 7 * T
+    return dict(conv_flops=2.0 * conv_mac * B, convtr_flops=2.0 * convtr_mac * B, post_flops=2.0 * post_mac * B,
+                act_elems=float(act_elems) * B)
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(frames, threads=None, warm_frames=16):
+    """audio-s/s of the oracle port (the reference's algorithm in torch fp32 on the host cores)."""
+    import torch
+    from oracle import bigvgan_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    h = O.indextts15_config()
+    sd = O.fold_weight_norm(O.make_state_dict(h, 0, "tame"))
+    with torch.no_grad():
+        lat, mel = O.synthetic_inputs(h, 1, warm_frames, TM, seed=1)
+        O.bigvgan_forward(lat, mel, sd, h)
+        lat, mel = O.synthetic_inputs(h, 1, frames, TM, seed=1)
+        t = time.perf_counter()
+        O.bigvgan_forward(lat, mel, sd, h)
+        dt = time.perf_counter() - t
+    return frames * UP / SR / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port; the Python
+    reference itself cannot travel to the GPU box) on all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import bigvgan_oracle as O
+    h = O.indextts15_config()
+    sd = O.fold_weight_norm(O.make_state_dict(h, 0, "tame"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    budget = 150.0
+    with torch.no_grad():
+        lat, mel = O.synthetic_inputs(h, 1, 16, TM, seed=1)
+        t = time.perf_counter(); O.bigvgan_forward(lat, mel, sd, h); t16 = time.perf_counter() - t
+        t = time.perf_counter(); O.bigvgan_forward(lat, mel, sd, h); t16 = min(t16, time.perf_counter() - t)
+        n_steps = args.steps + args.warmup
+        frames = int(max(16, min(T0, 16 * budget / max(t16 * n_steps, 1e-6))))
+        lat, mel = O.synthetic_inputs(h, 1, frames, TM, seed=1)
+        for _ in range(args.warmup):
+            O.bigvgan_forward(lat, mel, sd, h)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            O.bigvgan_forward(lat, mel, sd, h)
+        dt = time.perf_counter() - t
+    val = args.steps * frames * UP / SR / dt
+    sample = f"1 utterance x {frames} latent frames ({frames * UP / SR:.2f} s audio) per step, fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": "bigvgan_decode_audio_seconds_per_second", "value": val,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"IndexTTS-1.5 BigVGAN decode, {B_PER_GPU} x 10 s utterances per GPU "
+                               f"(T0={T0}, Tm={TM}); reference arm runs a bounded sample on the host CPU"},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import index_tts_ipex_b200 as pkg
+    from oracle import bigvgan_oracle as O      # only for synthetic weights/inputs and the CPU baseline leg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    h = O.indextts15_config()
+    sd = O.make_state_dict(h, 0, "tame")
+    m = pkg.BigVGAN(h, use_cuda_kernel=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    m.remove_weight_norm()
+    m.precision = args.precision
+    lat_h, mel_h = O.synthetic_inputs(h, B, T0, TM, seed=1 + rank)
+    lat_h, mel_h = lat_h.pin_memory(), mel_h.pin_memory()
+    lat, mel = lat_h.to(dev), mel_h.to(dev)
+    L = T0 * UP
+    gathered = torch.empty(world, B, 1, L, device=dev) if world > 1 else None
+
+    def step():
+        wav = m.decode(lat, mel_ref=mel)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(world * B, 1, L), wav)
+        return wav
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pkg.capi.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = pkg.capi.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    nl = torch.tensor([float(launches)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    total_ms = float(ms.item())
+    value = world * B * AUDIO_S_PER_UTT * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public host-buffer API: pinned H2D + decode + D2H every step
+    for _ in range(2):
+        m.decode_host(lat_h, mel_h, dev)
+    barrier()
+    t = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        out_h = m.decode_host(lat_h, mel_h, dev)          # synchronises the stream before returning
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t) * 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * AUDIO_S_PER_UTT * n_e2e / (float(e2e_ms.item()) / 1e3)
+    h2d = lat_h.numel() * 4 + mel_h.numel() * 4
+    d2h = out_h.numel() * out_h.element_size()
+
+    # ---- per-kernel-class device time inside one more step (CUDA events on the launch stream)
+    barrier()
+    pkg.capi.profile_begin()
+    n_prof = 2
+    for _ in range(n_prof):
+        m.decode(lat, mel_ref=mel)
+    prof = pkg.capi.profile_end()
+    if rank == 0:
+        work = algorithmic_work(h, B, T0)
+        pk = peaks()
+        es = 2 if args.precision == "bf16" else 4
+        per_step = {k: (v[0] / n_prof, v[1] // n_prof) for k, v in prof.items()}
+        kernel_ms = sum(v[0] for v in per_step.values())
+        dom = max(per_step, key=lambda k: per_step[k][0])
+        conv_ms, conv_n = per_step["conv1d"]
+        act_ms, act_n = per_step["act1d"]
+        conv_tf = work["conv_flops"] / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        act_gbs = 2.0 * work["act_elems"] * es / (act_ms / 1e3) / 1e9 if act_ms > 0 else 0.0
+        if dom == "act1d":
+            roof = {"kernel": "act1d_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": act_gbs / pk["hbm"], "traffic": None}
+        else:
+            roof = {"kernel": "conv1d (all dense generator convs)", "bound": "tensor", "achieved": conv_tf,
+                    "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / pk["tf_sustained"], "traffic": None}
+        roof["peak_source"] = pk["src"] + (" sustained" if roof["bound"] == "tensor" else " copy")
+        roof["launches_per_step"] = per_step[dom][1]
+        roof["avg_launch_ms"] = per_step[dom][0] / max(per_step[dom][1], 1)
+        roof["share_of_step_kernel_time"] = per_step[dom][0] / kernel_ms if kernel_ms else None
+        cpu_val, cpu_dt, cores = cpu_reference_rate(args.cpu_frames)
+        line = {
+            "metric": "bigvgan_decode_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"IndexTTS-1.5 BigVGAN decode (random init), {B} x 10 s utterances per GPU "
+                                   f"(T0={T0} latent frames, Tm={TM} mel frames), {args.precision} storage, "
+                                   f"utterance-sharded; N>1 adds one NCCL all_gather of the fp32 waveforms per step",
+                       "global_batch": world * B, "audio_s_per_step": world * B * AUDIO_S_PER_UTT,
+                       "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": n_e2e, "api": "BigVGAN.decode_host -> bvg_decode_host (pinned host buffers)"},
+            "gpu_launches": int(nl.item()),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_classes_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in per_step.items()},
+            "roofline_act1d": {"bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": act_gbs / pk["hbm"], "bytes_per_step": 2.0 * work["act_elems"] * es,
+                               "launches_per_step": act_n},
+            "roofline_conv": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                              "frac": conv_tf / pk["tf_sustained"], "flops_per_step": work["conv_flops"],
+                              "launches_per_step": conv_n},
+            "cpu_baseline": {"value": cpu_val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": f"1 utterance x {args.cpu_frames} latent frames "
+                                       f"({args.cpu_frames * UP / SR:.2f} s audio), fp32 oracle port, {cpu_dt:.1f} s"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default: the benchmark's 32)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-frames", type=int, default=200, help="latent frames of the CPU-baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * bigvgan_b200.h -- C ABI of libbigvgan_b200.so: a B200 (sm_100a) implementation of the
+ * IndexTTS BigVGAN vocoder decode path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain pointers, sizes and a
+ * cudaStream_t (passed as void*); there are no torch types.  All functions return 0 on
+ * success and a non-zero code on failure; bvg_last_error() returns a thread-local message
+ * (the Python wrapper raises RuntimeError with it, mirroring AT_ERROR -> RuntimeError in the
+ * reference's dispatch macro, alias_free_activation/cuda/type_shim.h:41-42).
+ *
+ * Ownership: the caller owns every input/output/workspace buffer (in practice torch tensors,
+ * passed by data_ptr()).  The library owns only what a bvg_plan holds (re-laid-out weights).
+ * No allocation and no synchronisation happens inside a *_fwd / bvg_decode call; work is
+ * enqueued on the caller's stream (the reference launches on the current torch stream,
+ * anti_alias_activation_cuda.cu:209).  Calls are re-entrant: scratch lives in the
+ * caller-provided workspace, so concurrent calls with distinct workspaces are safe
+ * (webui.py:441-452 runs one thread per request against one shared engine).
+ *
+ * Reference paths are relative to /root/reference/indextts/BigVGAN/.
+ */
+#ifndef BIGVGAN_B200_H_
+#define BIGVGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BVG_API __attribute__((visibility("default")))
+#else
+#define BVG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of activation tensors */
+enum { BVG_F32 = 0, BVG_BF16 = 1, BVG_F16 = 2 };
+
+/* status codes */
+enum {
+  BVG_OK = 0,
+  BVG_ERR_INVALID = 1,   /* bad argument / unsupported shape        */
+  BVG_ERR_CUDA = 2,      /* a CUDA runtime/driver call failed       */
+  BVG_ERR_STATE = 3,     /* plan not finalised / missing weight     */
+  BVG_ERR_WORKSPACE = 4  /* workspace too small                     */
+};
+
+BVG_API const char* bvg_last_error(void);
+/* library + build identification, e.g. "bigvgan_b200 0.1 sm_100a" */
+BVG_API const char* bvg_version(void);
+/* number of kernels this library launched from the calling thread since the last reset
+   (bench.py reports it as gpu_launches) */
+BVG_API int64_t bvg_launch_count(void);
+BVG_API void bvg_launch_count_reset(void);
+/* Per-kernel-class device timing for bench.py's roofline figure: between begin and end every
+   kernel launched from the calling thread is bracketed by CUDA events on its stream.
+   bvg_profile_end synchronises those events and returns, per class, the summed kernel time (ms)
+   and the launch count.  Classes: 0 Activation1d, 1 dense Conv1d (generator), 2 ConvTranspose1d,
+   3 everything else (speaker encoder, cond vectors, conv_post).  Arrays have 4 entries. */
+BVG_API void bvg_profile_begin(void);
+BVG_API int bvg_profile_end(float* ms_per_class, int64_t* launches_per_class);
+
+/* ------------------------------------------------------------------------------------------
+ * Op boundary: the reference's one native op.
+ *   replaces  anti_alias_activation_cuda.forward(inputs, up_ftr, down_ftr, alpha, beta)
+ *             (alias_free_activation/cuda/anti_alias_activation.cpp:19-23,
+ *              anti_alias_activation_cuda.cu:214-256)
+ * Semantics follow the PyTorch module (alias_free_torch/act.py:24-29), including its edge
+ * behaviour (replicate padding of the input for the up-FIR and of the ACTIVATED signal for the
+ * down-FIR), which the reference CUDA kernel does not reproduce at the first/last 3 samples.
+ *   src/dst  : [B, C, T] contiguous, dtype in {BVG_F32, BVG_BF16, BVG_F16}; dst != src
+ *   alpha_log, beta_log : fp32 [C], log-scale (the kernel applies exp, like .cu:89-90)
+ *   up_taps/down_taps   : fp32 [12] (device or host pointer is NOT accepted: pass HOST
+ *                         pointers; they are validated against the compiled-in taps with
+ *                         1e-6 tolerance; NULL skips validation)
+ *   precise  : 1 = libdevice sinf/expf (fp32 parity path), 0 = range-reduced MUFU path
+ * ------------------------------------------------------------------------------------------ */
+BVG_API int bvg_act1d_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                  const float* up_taps_host, const float* down_taps_host,
+                  int64_t B, int64_t C, int64_t T, int dtype, int precise, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layer-level entry points (parity tests call these through ctypes).
+ *   conv1d : torch.nn.Conv1d forward, stride 1, "same" length, zero padding (generator convs,
+ *            models.py:25-42,149,184) or reflect padding (ECAPA, nnet/CNN.py:458-488).
+ *            weight [Cout, Cin, K] fp32 (torch layout, device), bias [Cout] fp32 or NULL.
+ *            out = (conv + bias + res1 + res2) * scale   (res1/res2 nullable, same shape as out)
+ *   convtr1d : torch.nn.ConvTranspose1d forward (models.py:155-161): weight [Cin, Cout, K]
+ *            fp32, stride u, padding (K-u)/2, plus a per-(b,co) additive term `cond`
+ *            ([Bc, Cout] fp32, Bc in {1,B}; nullable) -- the speaker conditioning add of
+ *            models.py:232-234.
+ * ------------------------------------------------------------------------------------------ */
+BVG_API int bvg_conv1d_fwd(void* dst, const void* src, const float* weight, const float* bias,
+                   const void* res1, const void* res2, float scale,
+                   int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation,
+                   int reflect_pad, int dtype, void* stream);
+BVG_API int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, const float* bias,
+                     const float* cond, int64_t Bc,
+                     int64_t B, int64_t Cin, int64_t Cout, int64_t Tin, int K, int stride,
+                     int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path plan.   replaces  indextts.BigVGAN.models.BigVGAN  (models.py:130-275) as built,
+ * loaded and called by infer.py:61-67,204,498.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_plan bvg_plan;
+
+typedef struct bvg_config {
+  int32_t gpt_dim;                  /* h.gpt_dim                      */
+  int32_t upsample_initial_channel; /* h.upsample_initial_channel     */
+  int32_t num_upsamples;            /* len(h.upsample_rates)  (<= 8)  */
+  int32_t upsample_rates[8];
+  int32_t upsample_kernel_sizes[8];
+  int32_t num_kernels;              /* len(h.resblock_kernel_sizes) (<= 4) */
+  int32_t resblock_kernel_sizes[4];
+  int32_t resblock_dilation_sizes[4][3];
+  int32_t speaker_embedding_dim;    /* h.speaker_embedding_dim        */
+  int32_t num_mels;                 /* h.num_mels                     */
+  int32_t cond_in_each_up_layer;    /* h.cond_d_vector_in_each_upsampling_layer */
+  int32_t snake_logscale;           /* h.snake_logscale               */
+  int32_t device;                   /* CUDA device ordinal            */
+} bvg_config;
+
+BVG_API int bvg_plan_create(bvg_plan** out, const bvg_config* cfg);
+BVG_API void bvg_plan_destroy(bvg_plan* plan);
+
+/* Upload one tensor of the (weight-norm-folded) state dict.  `key` is the reference's
+ * state-dict key after remove_weight_norm (models.py:252-260), e.g. "conv_pre.weight",
+ * "resblocks.3.convs1.0.bias", "resblocks.3.activations.2.act.alpha",
+ * "speaker_encoder.blocks.0.norm.norm.running_var", "conds.2.weight".
+ * `data` is a HOST fp32 pointer with `numel` elements in torch's contiguous layout. */
+BVG_API int bvg_plan_set_tensor(bvg_plan* plan, const char* key, const float* data, int64_t numel);
+/* Validates that every tensor the config requires was supplied, folds eval BatchNorm and
+ * builds the device-side layouts (SIMT fp32 packs and, when `enable_bf16_umma` != 0, the bf16
+ * per-tap K-major packs the tcgen05 path consumes). */
+BVG_API int bvg_plan_finalize(bvg_plan* plan, int enable_bf16_umma);
+
+/* workspace the decode call needs for (B utterances, T0 latent frames, Tm mel frames) in
+ * precision `dtype` (BVG_F32: fp32 storage + fp32 CUDA-core math; BVG_BF16: bf16 storage,
+ * tcgen05 bf16 convs with fp32 accumulate) */
+BVG_API size_t bvg_workspace_bytes(const bvg_plan* plan, int64_t B, int64_t T0, int64_t Tm, int dtype);
+
+/* speaker encoder only:  mel [Bm, Tm, num_mels] fp32 device -> spk [Bm, emb] fp32 device
+ * (ECAPA_TDNN.forward, ECAPA_TDNN.py:543-581, lengths=None) */
+BVG_API int bvg_speaker_embed(const bvg_plan* plan, const float* mel, int64_t Bm, int64_t Tm,
+                      float* spk, void* workspace, size_t workspace_bytes, void* stream);
+
+/* BigVGAN.forward (models.py:201-250).
+ *   latent [B, T0, gpt_dim] fp32 device; exactly one of {mel, spk} non-NULL:
+ *   mel [Bm, Tm, num_mels] fp32 device (Bm in {1, B}) or a precomputed spk [Bm, emb] fp32.
+ *   wav  [B, 1, T0*prod(rates)]  fp32 device  (tanh output), or
+ *   when pcm16 != NULL: additionally the caller epilogue of infer.py:206-212,234 fused:
+ *   pcm16[B, L] = int16(clamp(32767*wav, -32767, 32767)); wav may then be NULL.
+ *   t_lo_pad/t_hi_pad: for chunked long-form decode -- latent frames at the start/end of this
+ *   call that are halo (their output samples are computed but not stored; wav then has
+ *   (T0 - t_lo_pad - t_hi_pad)*prod(rates) samples per utterance).  0,0 for a plain call. */
+BVG_API int bvg_decode(const bvg_plan* plan, const float* latent, const float* mel, const float* spk,
+               int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype,
+               float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers: copies latent/mel host->device, decodes, copies the waveform
+ * back (the end-to-end figure bench.py reports as `e2e`).  Uses the plan's device and the
+ * given stream; synchronises the stream before returning.  latent/mel/wav should be pinned. */
+BVG_API int bvg_decode_host(const bvg_plan* plan, const float* latent_host, const float* mel_host,
+                    int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype,
+                    float* wav_host, int16_t* pcm16_host,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGVGAN_B200_H_ */

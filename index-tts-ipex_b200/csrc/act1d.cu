@@ -1,0 +1,335 @@
+// Activation1d for sm_100a:  2x kaiser-sinc upsample -> SnakeBeta -> 2x low-pass downsample,
+// fused into one stencil pass that never materialises the 2x intermediate.
+//
+// Restates (does not port) alias_free_torch/act.py:24-29 = resample.py:25-33 ->
+// activations.py:109-122 -> resample.py:46-49 / filter.py:87-96 of the reference, with the
+// PyTorch path's edge semantics (replicate padding of x before the up-FIR, replicate padding
+// of the ACTIVATED signal before the down-FIR).  The reference's own CUDA kernel
+// (anti_alias_activation_cuda.cu:43-181) deviates from that at the first/last 3 samples.
+//
+// Closed form, f = 12 symmetric taps (bvg_common.cuh), per row x[0..T):
+//   u[2j]   = 2*sum_{d=-3..2} f[5-2d] * x[clamp(j+d)]
+//   u[2j+1] = 2*sum_{d=-2..3} f[6-2d] * x[clamp(j+d)]
+//   a[m]    = u[m] + 1/(exp(beta)+1e-9) * sin(exp(alpha)*u[m])^2
+//   y[t]    = sum_{k=0..11} f[k] * a[clamp(2t+k-5, 0, 2T-1)]
+//
+// Data movement: one CTA = 8 rows x 256 samples.  The tile plus an 8-sample halo per side is
+// staged in shared memory by the TMA unit (cp.async.bulk, one bulk copy per row, completion
+// on an mbarrier) when rows are 16-byte aligned; each thread then owns 8 consecutive outputs:
+// three 128-bit conflict-free LDS for its 24-sample window (bf16), all FIR/activation math in
+// registers, one 128-bit coalesced store.  HBM sees each element once in, once out.
+#include "bvg_common.cuh"
+
+namespace bvg {
+
+namespace {
+
+constexpr int kRows = 8;      // rows per CTA
+constexpr int kW = 256;       // outputs per row per CTA
+constexpr int kHalo = 8;      // staged halo per side (5 needed; 8 keeps 16B alignment)
+constexpr int kPitch = kW + 2 * kHalo;   // 272 elements
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <bool PRECISE>
+__device__ __forceinline__ float snake(float u, float ea, float ib) {
+  if (PRECISE) {
+    float s = sinf(u * ea);
+    return fmaf(ib * s, s, u);
+  } else {
+    // sin^2 has period pi: reduce z = u*ea to r in [-pi/2, pi/2] with a 2-term Cody-Waite
+    // split of pi, then MUFU.SIN (accurate to ~1e-7 abs on that interval).
+    float z = u * ea;
+    float k = rintf(z * 0.318309886183790672f);
+    float r = fmaf(k, -3.140625f, z);
+    r = fmaf(k, -9.67653589793e-4f, r);
+    float s = __sinf(r);
+    return fmaf(ib * s, s, u);
+  }
+}
+
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+// load 24 consecutive elements starting at a 16B-aligned smem address
+template <typename T> __device__ __forceinline__ void load_window(const T* p, float (&xw)[24]);
+template <> __device__ __forceinline__ void load_window<float>(const float* p, float (&xw)[24]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float4 v = q[i];
+    xw[4 * i + 0] = v.x; xw[4 * i + 1] = v.y; xw[4 * i + 2] = v.z; xw[4 * i + 3] = v.w;
+  }
+}
+template <> __device__ __forceinline__ void load_window<__nv_bfloat16>(const __nv_bfloat16* p, float (&xw)[24]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    uint4 v = q[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      xw[8 * i + 2 * j + 0] = __uint_as_float(w[j] << 16);
+      xw[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+template <> __device__ __forceinline__ void load_window<__half>(const __half* p, float (&xw)[24]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    uint4 v = q[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      xw[8 * i + 2 * j + 0] = f2.x;
+      xw[8 * i + 2 * j + 1] = f2.y;
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ void store8_vec(T* p, const float (&y)[8]);
+template <> __device__ __forceinline__ void store8_vec<float>(float* p, const float (&y)[8]) {
+  float4* q = reinterpret_cast<float4*>(p);
+  q[0] = make_float4(y[0], y[1], y[2], y[3]);
+  q[1] = make_float4(y[4], y[5], y[6], y[7]);
+}
+template <> __device__ __forceinline__ void store8_vec<__nv_bfloat16>(__nv_bfloat16* p, const float (&y)[8]) {
+  uint4 v;
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(y[0], y[1]);
+  __nv_bfloat162 b1 = __floats2bfloat162_rn(y[2], y[3]);
+  __nv_bfloat162 b2 = __floats2bfloat162_rn(y[4], y[5]);
+  __nv_bfloat162 b3 = __floats2bfloat162_rn(y[6], y[7]);
+  v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+  v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store8_vec<__half>(__half* p, const float (&y)[8]) {
+  uint4 v;
+  __half2 b0 = __floats2half2_rn(y[0], y[1]);
+  __half2 b1 = __floats2half2_rn(y[2], y[3]);
+  __half2 b2 = __floats2half2_rn(y[4], y[5]);
+  __half2 b3 = __floats2half2_rn(y[6], y[7]);
+  v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+  v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// The per-thread stencil: 24-sample input window (xw[i] = x[tg-8+i]) -> 8 outputs y[tg..tg+7].
+// Shared by the plain [B,C,T] kernel below.
+template <bool PRECISE>
+__device__ __forceinline__ void act1d_window(float (&xw)[24], float (&y)[8], float ea, float ib,
+                                             int64_t tg, int64_t T) {
+  // replicate padding of the input (F.pad(x,(5,5),'replicate'), resample.py:28)
+  if (tg - 5 < 0 || tg + 12 > T - 1) {
+    float xl = 0.f, xr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      int64_t t = tg - 8 + i;
+      if (t == 0) xl = xw[i];
+      if (t == T - 1) xr = xw[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      int64_t t = tg - 8 + i;
+      if (t < 0) xw[i] = xl;
+      if (t > T - 1) xw[i] = xr;
+    }
+  }
+  const float g0 = 2.f * BVG_F0, g1 = 2.f * BVG_F1, g2 = 2.f * BVG_F2, g3 = 2.f * BVG_F3,
+              g4 = 2.f * BVG_F4, g5 = 2.f * BVG_F5;
+  // a[i] <-> upsampled index m = 2*tg - 5 + i, i = 0..25
+  float a[26];
+#pragma unroll
+  for (int i = 0; i < 26; ++i) {
+    float u;
+    if ((i & 1) == 0) {
+      // m odd = 2j+1, j = tg-3+i/2 -> xw index of x[j] is j-tg+8 = 5+i/2
+      const int c = 5 + i / 2;
+      u = g1 * xw[c - 2];
+      u = fmaf(g3, xw[c - 1], u);
+      u = fmaf(g5, xw[c], u);
+      u = fmaf(g4, xw[c + 1], u);
+      u = fmaf(g2, xw[c + 2], u);
+      u = fmaf(g0, xw[c + 3], u);
+    } else {
+      // m even = 2j, j = tg-2+(i-1)/2 -> xw index 6+(i-1)/2
+      const int c = 6 + (i - 1) / 2;
+      u = g0 * xw[c - 3];
+      u = fmaf(g2, xw[c - 2], u);
+      u = fmaf(g4, xw[c - 1], u);
+      u = fmaf(g5, xw[c], u);
+      u = fmaf(g3, xw[c + 1], u);
+      u = fmaf(g1, xw[c + 2], u);
+    }
+    a[i] = snake<PRECISE>(u, ea, ib);
+  }
+  // replicate padding of the ACTIVATED signal (F.pad(x,(5,6),'replicate'), filter.py:90-92)
+  const int64_t m0 = 2 * tg - 5;
+  if (m0 < 0 || m0 + 25 > 2 * T - 1) {
+    float al = 0.f, ar = 0.f;
+#pragma unroll
+    for (int i = 0; i < 26; ++i) {
+      if (m0 + i == 0) al = a[i];
+      if (m0 + i == 2 * T - 1) ar = a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 26; ++i) {
+      if (m0 + i < 0) a[i] = al;
+      if (m0 + i > 2 * T - 1) a[i] = ar;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = 2 * q;
+    // symmetric taps: f[k] == f[11-k]
+    float s = BVG_F0 * (a[i] + a[i + 11]);
+    s = fmaf(BVG_F1, a[i + 1] + a[i + 10], s);
+    s = fmaf(BVG_F2, a[i + 2] + a[i + 9], s);
+    s = fmaf(BVG_F3, a[i + 3] + a[i + 8], s);
+    s = fmaf(BVG_F4, a[i + 4] + a[i + 7], s);
+    s = fmaf(BVG_F5, a[i + 5] + a[i + 6], s);
+    y[q] = s;
+  }
+}
+
+template <typename T, bool PRECISE, bool ALIGNED>
+__global__ void __launch_bounds__(kThreads)
+act1d_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __restrict__ alpha_log,
+             const float* __restrict__ beta_log, int64_t rows, int C, int64_t Tlen, int col_tiles) {
+  __shared__ __align__(128) T tile[kRows][kPitch];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int tid = threadIdx.x;
+  const int64_t blk = blockIdx.x;
+  const int64_t row0 = (blk / col_tiles) * kRows;
+  const int64_t t0 = (blk % col_tiles) * (int64_t)kW;
+  const int nrows = (int)min((int64_t)kRows, rows - row0);
+
+  if (ALIGNED) {
+    // rows are 16B aligned and T is a multiple of the 16B vector width: TMA bulk copies.
+    const int64_t lo = max(t0 - kHalo, (int64_t)0);
+    const int64_t hi = min(t0 + kW + kHalo, Tlen);
+    const uint32_t bytes = (uint32_t)((hi - lo) * sizeof(T));
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, bytes * nrows);
+      for (int r = 0; r < nrows; ++r)
+        bulk_g2s(&tile[r][lo - (t0 - kHalo)], src + (row0 + r) * Tlen + lo, bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int idx = tid; idx < kRows * kPitch; idx += kThreads) {
+      const int r = idx / kPitch, c = idx % kPitch;
+      const int64_t t = t0 - kHalo + c;
+      T v = from_f<T>(0.f);
+      if (r < nrows && t >= 0 && t < Tlen) v = src[(row0 + r) * Tlen + t];
+      tile[r][c] = v;
+    }
+    __syncthreads();
+  }
+
+  const int r = tid >> 5;
+  const int c0 = (tid & 31) * 8;
+  const int64_t tg = t0 + c0;
+  if (r >= nrows || tg >= Tlen) return;
+  const int64_t row = row0 + r;
+  const int ch = (int)(row % C);
+  float ea, ib;
+  if (PRECISE) {
+    ea = expf(alpha_log[ch]);
+    ib = 1.0f / (expf(beta_log[ch]) + 1e-9f);
+  } else {
+    ea = __expf(alpha_log[ch]);
+    ib = __fdividef(1.0f, __expf(beta_log[ch]) + 1e-9f);
+  }
+  float xw[24], y[8];
+  load_window<T>(&tile[r][c0], xw);
+  act1d_window<PRECISE>(xw, y, ea, ib, tg, Tlen);
+  T* out = dst + row * Tlen + tg;
+  if (ALIGNED) {
+    store8_vec<T>(out, y);       // T % (16/sizeof(T)) == 0 and tg % 8 == 0 -> all 8 in range
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (tg + q < Tlen) out[q] = from_f<T>(y[q]);
+  }
+}
+
+template <typename T>
+int launch_typed(void* dst, const void* src, const float* a, const float* b, int64_t rows, int64_t C,
+                 int64_t Tlen, int precise, cudaStream_t st) {
+  const int64_t col_tiles = (Tlen + kW - 1) / kW;
+  const int64_t row_groups = (rows + kRows - 1) / kRows;
+  const int64_t nblk = col_tiles * row_groups;
+  BVG_CHECK_ARG(nblk < (1ll << 31) && col_tiles < (1ll << 31), "act1d: problem too large (%lld CTAs)", (long long)nblk);
+  // vector path needs 8-element granularity on the store (8 outputs/thread) and 16B-aligned rows
+  const bool aligned = (Tlen % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  dim3 grid((unsigned)nblk), block(kThreads);
+  ProfScope prof(st, KC_ACT1D);
+  T* d = static_cast<T*>(dst);
+  const T* s = static_cast<const T*>(src);
+#define BVG_ACT_LAUNCH(P, A) act1d_kernel<T, P, A><<<grid, block, 0, st>>>(d, s, a, b, rows, (int)C, Tlen, (int)col_tiles)
+  if (precise) { if (aligned) BVG_ACT_LAUNCH(true, true); else BVG_ACT_LAUNCH(true, false); }
+  else         { if (aligned) BVG_ACT_LAUNCH(false, true); else BVG_ACT_LAUNCH(false, false); }
+#undef BVG_ACT_LAUNCH
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace
+
+int act1d_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                 int64_t B, int64_t C, int64_t T, int dtype, int precise, cudaStream_t st) {
+  BVG_CHECK_ARG(dst && src && alpha_log && beta_log, "act1d: null pointer");
+  BVG_CHECK_ARG(dst != src, "act1d: in-place is not supported (halo reads would race)");
+  BVG_CHECK_ARG(B >= 0 && C > 0 && T >= 0 && C < (1ll << 31), "act1d: bad shape B=%lld C=%lld T=%lld", (long long)B, (long long)C, (long long)T);
+  if (B == 0 || T == 0) return BVG_OK;
+  const int64_t rows = B * C;
+  switch (dtype) {
+    case BVG_F32: return launch_typed<float>(dst, src, alpha_log, beta_log, rows, C, T, precise, st);
+    case BVG_BF16: return launch_typed<__nv_bfloat16>(dst, src, alpha_log, beta_log, rows, C, T, precise, st);
+    case BVG_F16: return launch_typed<__half>(dst, src, alpha_log, beta_log, rows, C, T, precise, st);
+    default: set_error("act1d: unsupported dtype %d", dtype); return BVG_ERR_INVALID;
+  }
+}
+
+}  // namespace bvg

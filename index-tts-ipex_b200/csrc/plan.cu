@@ -1,0 +1,679 @@
+// Plan (weights + layer graph) and the C ABI of libbigvgan_b200.
+//
+// A bvg_plan mirrors what `IndexTTS.__init__` builds at infer.py:61-67: the generator of
+// BigVGAN/models.py:130-275 with weight norm already folded (models.py:252-260), every tensor
+// supplied under its reference state-dict key.  bvg_decode() enqueues BigVGAN.forward
+// (models.py:201-250) on the caller's stream: ECAPA speaker encoder -> conv_pre + cond ->
+// 6 x (ConvTranspose1d + cond + mean of 3 AMPBlock1) -> Activation1d -> conv_post -> tanh.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bvg_common.cuh"
+
+namespace bvg {
+
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+
+// profiler state (per calling thread)
+struct ProfRec { int kc; cudaEvent_t a, b; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof_recs;
+thread_local std::vector<cudaEvent_t> g_prof_pool;
+
+void prof_mark(cudaStream_t st, int kclass, bool begin) {
+  if (!g_prof_on) return;
+  if (begin) {
+    ProfRec r;
+    r.kc = kclass;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+      if (!g_prof_pool.empty()) { *e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+      else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.a, st);
+    g_prof_recs.push_back(r);
+  } else if (!g_prof_recs.empty()) {
+    cudaEventRecord(g_prof_recs.back().b, st);
+  }
+}
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+struct ConvLayer {
+  float* w = nullptr;     // [K][Cin][Cout] fp32
+  float* bias = nullptr;  // [Cout] or null
+  int Cin = 0, Cout = 0, K = 1;
+};
+struct Tdnn {             // conv -> ReLU -> eval-BN (ECAPA_TDNN.py:126-128)
+  ConvLayer conv;
+  float* bn_scale = nullptr;
+  float* bn_shift = nullptr;
+  int dil = 1;
+};
+struct ResBlock {         // AMPBlock1 (models.py:20-80)
+  ConvLayer c1[3], c2[3];
+  float* alpha[6] = {};
+  float* beta[6] = {};
+  int K = 3;
+  int dil[3] = {1, 3, 5};
+};
+struct SERes2 {           // SERes2NetBlock (ECAPA_TDNN.py:341-426)
+  Tdnn tdnn1, r2n[7], tdnn2;
+  ConvLayer se1, se2;
+};
+
+}  // namespace bvg
+
+using namespace bvg;
+
+struct bvg_plan {
+  bvg_config cfg{};
+  std::map<std::string, std::vector<float>> host;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  int n_stage = 0;
+  int C[9] = {};          // C[0] = upsample_initial_channel, C[i+1] = channels after ups[i]
+  int64_t total_up = 1;
+  // generator
+  ConvLayer conv_pre, cond_layer;
+  std::vector<ConvLayer> ups, conds;
+  std::vector<ResBlock> res;
+  float *post_alpha = nullptr, *post_beta = nullptr, *post_w = nullptr, *post_bias = nullptr;
+  // speaker encoder (ECAPA_TDNN.py:429-541, default channels [512,512,512,512,1536])
+  Tdnn e_block0, e_mfa, e_asp_tdnn;
+  SERes2 e_blk[3];
+  ConvLayer e_asp_ctx, e_asp_conv, e_fc;
+  float *asp_bn_scale = nullptr, *asp_bn_shift = nullptr;
+};
+
+namespace {
+
+constexpr int kEC = 512;      // ECAPA trunk channels
+constexpr int kEM = 1536;     // MFA channels
+constexpr int kEA = 128;      // attention / SE bottleneck channels
+
+int dev_alloc(bvg_plan* P, void** out, size_t bytes) {
+  BVG_CUDA(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+  P->allocs.push_back(*out);
+  return BVG_OK;
+}
+
+int upload(bvg_plan* P, const float* h, int64_t n, float** out) {
+  void* d = nullptr;
+  BVG_TRY(dev_alloc(P, &d, n * sizeof(float)));
+  BVG_CUDA(cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = static_cast<float*>(d);
+  return BVG_OK;
+}
+
+int get_host(bvg_plan* P, const std::string& key, int64_t numel, const std::vector<float>** out) {
+  auto it = P->host.find(key);
+  if (it == P->host.end()) {
+    set_error("plan: missing state-dict tensor '%s'", key.c_str());
+    return BVG_ERR_STATE;
+  }
+  if ((int64_t)it->second.size() != numel) {
+    set_error("plan: tensor '%s' has %lld elements, expected %lld", key.c_str(), (long long)it->second.size(),
+              (long long)numel);
+    return BVG_ERR_STATE;
+  }
+  *out = &it->second;
+  return BVG_OK;
+}
+
+int upload_key(bvg_plan* P, const std::string& key, int64_t numel, float** out) {
+  const std::vector<float>* v;
+  BVG_TRY(get_host(P, key, numel, &v));
+  return upload(P, v->data(), numel, out);
+}
+
+// weight key holds torch layout [Cout,Cin,K] (or [Cin,Cout,K] when transposed); optional input-channel slice
+int make_conv(bvg_plan* P, const std::string& wkey, const std::string& bkey, int Cout, int Cin_total, int K,
+              bool transposed, ConvLayer* L, int ci_lo = 0, int ci_hi = -1) {
+  if (ci_hi < 0) ci_hi = Cin_total;
+  const int Cin = ci_hi - ci_lo;
+  const std::vector<float>* w;
+  BVG_TRY(get_host(P, wkey, (int64_t)Cout * Cin_total * K, &w));
+  float* raw = nullptr;
+  const int64_t n = (int64_t)Cout * Cin * K;
+  if (ci_lo == 0 && ci_hi == Cin_total) {
+    BVG_CUDA(cudaMalloc(&raw, n * sizeof(float)));
+    BVG_CUDA(cudaMemcpy(raw, w->data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    if (transposed) { set_error("plan: sliced transposed conv unsupported"); return BVG_ERR_INVALID; }
+    std::vector<float> tmp(n);
+    for (int co = 0; co < Cout; ++co)
+      memcpy(&tmp[(size_t)co * Cin * K], &(*w)[((size_t)co * Cin_total + ci_lo) * K], (size_t)Cin * K * sizeof(float));
+    BVG_CUDA(cudaMalloc(&raw, n * sizeof(float)));
+    BVG_CUDA(cudaMemcpy(raw, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  void* d = nullptr;
+  int rc = dev_alloc(P, &d, n * sizeof(float));
+  if (rc == BVG_OK) rc = repack_conv_weight_launch((float*)d, raw, Cout, Cin, K, transposed ? 1 : 0, 0);
+  cudaError_t e = cudaStreamSynchronize(0);
+  cudaFree(raw);
+  if (rc != BVG_OK) return rc;
+  BVG_CUDA(e);
+  L->w = (float*)d;
+  L->Cin = Cin; L->Cout = Cout; L->K = K;
+  L->bias = nullptr;
+  if (!bkey.empty()) BVG_TRY(upload_key(P, bkey, Cout, &L->bias));
+  return BVG_OK;
+}
+
+// eval BatchNorm1d folded to y = x*scale + shift (nnet/normalization.py:75-108, eps 1e-5)
+int make_bn(bvg_plan* P, const std::string& p, int Cn, float** scale, float** shift) {
+  const std::vector<float>*w, *b, *m, *v;
+  BVG_TRY(get_host(P, p + ".weight", Cn, &w));
+  BVG_TRY(get_host(P, p + ".bias", Cn, &b));
+  BVG_TRY(get_host(P, p + ".running_mean", Cn, &m));
+  BVG_TRY(get_host(P, p + ".running_var", Cn, &v));
+  std::vector<float> sc(Cn), sh(Cn);
+  for (int i = 0; i < Cn; ++i) {
+    sc[i] = (*w)[i] / sqrtf((*v)[i] + 1e-5f);
+    sh[i] = (*b)[i] - (*m)[i] * sc[i];
+  }
+  BVG_TRY(upload(P, sc.data(), Cn, scale));
+  BVG_TRY(upload(P, sh.data(), Cn, shift));
+  return BVG_OK;
+}
+
+int make_tdnn(bvg_plan* P, const std::string& p, int Cin, int Cout, int K, int dil, Tdnn* t, int ci_lo = 0,
+              int ci_hi = -1) {
+  BVG_TRY(make_conv(P, p + ".conv.conv.weight", p + ".conv.conv.bias", Cout, Cin, K, false, &t->conv, ci_lo, ci_hi));
+  BVG_TRY(make_bn(P, p + ".norm.norm", Cout, &t->bn_scale, &t->bn_shift));
+  t->dil = dil;
+  return BVG_OK;
+}
+
+// Activation1d buffers must be the compiled-in kaiser-sinc taps (they are persistent buffers in the
+// reference state dict: alias_free_torch/resample.py:22, filter.py:82)
+int check_taps(bvg_plan* P, const std::string& key) {
+  static const float ref[12] = {BVG_F0, BVG_F1, BVG_F2, BVG_F3, BVG_F4, BVG_F5,
+                                BVG_F5, BVG_F4, BVG_F3, BVG_F2, BVG_F1, BVG_F0};
+  auto it = P->host.find(key);
+  if (it == P->host.end()) return BVG_OK;  // buffers are optional (older checkpoints omit them)
+  if (it->second.size() != 12) { set_error("plan: '%s' must have 12 taps", key.c_str()); return BVG_ERR_STATE; }
+  for (int i = 0; i < 12; ++i)
+    if (fabsf(it->second[i] - ref[i]) > 1e-6f) {
+      set_error("plan: '%s' differs from kaiser_sinc_filter1d(0.25,0.3,12) at tap %d (%g vs %g); only the "
+                "reference's default Activation1d filter is supported", key.c_str(), i, it->second[i], ref[i]);
+      return BVG_ERR_STATE;
+    }
+  return BVG_OK;
+}
+
+int make_act(bvg_plan* P, const std::string& p, int Cn, float** alpha, float** beta) {
+  const std::vector<float>*a, *b;
+  BVG_TRY(get_host(P, p + ".act.alpha", Cn, &a));
+  BVG_TRY(get_host(P, p + ".act.beta", Cn, &b));
+  BVG_TRY(check_taps(P, p + ".upsample.filter"));
+  BVG_TRY(check_taps(P, p + ".downsample.lowpass.filter"));
+  std::vector<float> la(*a), lb(*b);
+  if (!P->cfg.snake_logscale) {  // kernel applies exp: cancel it (cuda/activation1d.py:67-71)
+    for (auto& x : la) x = logf(x);
+    for (auto& x : lb) x = logf(x);
+  }
+  BVG_TRY(upload(P, la.data(), Cn, alpha));
+  BVG_TRY(upload(P, lb.data(), Cn, beta));
+  return BVG_OK;
+}
+
+struct Bump {
+  char* base;
+  size_t cap, off = 0;
+  bool overflow = false;
+  Bump(void* p, size_t c) : base(static_cast<char*>(p)), cap(c) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    void* r = base ? base + off : nullptr;
+    off += bytes;
+    if (off > cap) overflow = true;
+    return r;
+  }
+  float* takef(int64_t n) { return static_cast<float*>(take((size_t)n * 4)); }
+};
+
+struct EcapaWs {
+  float *X0, *Y1, *Y2, *Y3, *XL, *M, *A1, *A2, *sem, *se1, *se2, *ms, *actx, *pooled;
+};
+void carve_ecapa(Bump& b, int64_t Bm, int64_t Tm, EcapaWs* w) {
+  w->X0 = b.takef(Bm * kEC * Tm); w->Y1 = b.takef(Bm * kEC * Tm); w->Y2 = b.takef(Bm * kEC * Tm);
+  w->Y3 = b.takef(Bm * kEC * Tm); w->XL = b.takef(Bm * kEM * Tm); w->M = b.takef(Bm * kEM * Tm);
+  w->A1 = b.takef(Bm * kEA * Tm); w->A2 = b.takef(Bm * kEM * Tm);
+  w->sem = b.takef(Bm * kEC); w->se1 = b.takef(Bm * kEA); w->se2 = b.takef(Bm * kEC);
+  w->ms = b.takef(Bm * 2 * kEM); w->actx = b.takef(Bm * kEA); w->pooled = b.takef(Bm * 2 * kEM);
+}
+
+// conv on [B,C,T]-contiguous fp32 tensors viewed through explicit strides
+int conv_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64_t sb, int64_t sc, int64_t st_,
+             const ConvLayer& L, ConvEpilogue ep, int64_t B, int64_t T, int dil, int pad_mode, cudaStream_t st) {
+  ep.bias = L.bias;
+  return conv1d_simt_launch(dst, dsb, src, src2, sb, sc, st_, L.w, ep, B, L.Cin, L.Cout, T, L.K, dil, pad_mode,
+                            BVG_F32, BVG_F32, st);
+}
+int tdnn_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64_t sb, int64_t sc, int64_t st_,
+             const Tdnn& t, int64_t B, int64_t T, cudaStream_t st, const float* cond = nullptr, int act = 0) {
+  ConvEpilogue ep;
+  ep.relu = 1; ep.post_scale = t.bn_scale; ep.post_shift = t.bn_shift; ep.act = act;
+  ep.cond = cond; ep.cond_B = B;
+  return conv_f32(dst, dsb, src, src2, sb, sc, st_, t.conv, ep, B, T, t.dil, 1, st);
+}
+
+// ECAPA_TDNN.forward (ECAPA_TDNN.py:543-581), lengths=None.  mel [Bm,Tm,num_mels] -> spk [Bm,E]
+int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, float* spk, const EcapaWs& w,
+                  cudaStream_t st) {
+  const int NM = P->cfg.num_mels;
+  BVG_CHECK_ARG(Tm >= 5, "speaker encoder: reference mel needs >= 5 frames for reflect padding (got %lld)", (long long)Tm);
+  // x.transpose(1,2): read channels-last mel through strides
+  BVG_TRY(tdnn_f32(w.X0, kEC * Tm, mel, nullptr, Tm * NM, 1, NM, P->e_block0, Bm, Tm, st));
+  const float* X = w.X0;
+  int64_t Xsb = kEC * Tm;
+  for (int i = 0; i < 3; ++i) {
+    const SERes2& S = P->e_blk[i];
+    BVG_TRY(tdnn_f32(w.Y1, kEC * Tm, X, nullptr, Xsb, Tm, 1, S.tdnn1, Bm, Tm, st));
+    // Res2NetBlock :179-191: 8 chunks of 64 channels, y_i = f(x_i + y_{i-1})
+    const int CH = kEC / 8;
+    BVG_CUDA(cudaMemcpy2DAsync(w.Y2, kEC * Tm * 4, w.Y1, kEC * Tm * 4, (size_t)CH * Tm * 4, Bm,
+                               cudaMemcpyDeviceToDevice, st));
+    for (int j = 1; j < 8; ++j) {
+      const float* s2 = (j >= 2) ? w.Y2 + (int64_t)(j - 1) * CH * Tm : nullptr;
+      BVG_TRY(tdnn_f32(w.Y2 + (int64_t)j * CH * Tm, kEC * Tm, w.Y1 + (int64_t)j * CH * Tm, s2, kEC * Tm, Tm, 1,
+                       S.r2n[j - 1], Bm, Tm, st));
+    }
+    BVG_TRY(tdnn_f32(w.Y3, kEC * Tm, w.Y2, nullptr, kEC * Tm, Tm, 1, S.tdnn2, Bm, Tm, st));
+    // SEBlock :228-242
+    BVG_TRY(row_mean_launch(w.sem, w.Y3, Bm * kEC, Tm, st));
+    ConvEpilogue e1; e1.relu = 1;
+    BVG_TRY(conv_f32(w.se1, kEA, w.sem, nullptr, kEC, 1, 1, S.se1, e1, Bm, 1, 1, 0, st));
+    ConvEpilogue e2; e2.act = 2;
+    BVG_TRY(conv_f32(w.se2, kEC, w.se1, nullptr, kEA, 1, 1, S.se2, e2, Bm, 1, 1, 0, st));
+    float* out = w.XL + (int64_t)i * kEC * Tm;
+    BVG_TRY(scale_residual_launch(out, kEM * Tm, w.se2, w.Y3, X, Xsb, Bm, kEC, Tm, st));
+    X = out; Xsb = kEM * Tm;
+  }
+  BVG_TRY(tdnn_f32(w.M, kEM * Tm, w.XL, nullptr, kEM * Tm, Tm, 1, P->e_mfa, Bm, Tm, st));
+  // AttentiveStatisticsPooling :282-338.  The tdnn over cat([x, mean, std]) splits into a conv over x
+  // plus a per-utterance term from (mean, std).
+  BVG_TRY(row_stats_launch(w.ms, w.M, Bm, kEM, Tm, st));
+  ConvEpilogue ec;
+  BVG_TRY(conv_f32(w.actx, kEA, w.ms, nullptr, 2 * kEM, 1, 1, P->e_asp_ctx, ec, Bm, 1, 1, 0, st));
+  BVG_TRY(tdnn_f32(w.A1, kEA * Tm, w.M, nullptr, kEM * Tm, Tm, 1, P->e_asp_tdnn, Bm, Tm, st, w.actx, /*tanh*/ 1));
+  ConvEpilogue ea;
+  BVG_TRY(conv_f32(w.A2, kEM * Tm, w.A1, nullptr, kEA * Tm, Tm, 1, P->e_asp_conv, ea, Bm, Tm, 1, 0, st));
+  BVG_TRY(attn_stats_launch(w.pooled, w.A2, w.M, P->asp_bn_scale, P->asp_bn_shift, Bm, kEM, Tm, st));
+  ConvEpilogue ef;
+  BVG_TRY(conv_f32(spk, P->cfg.speaker_embedding_dim, w.pooled, nullptr, 2 * kEM, 1, 1, P->e_fc, ef, Bm, 1, 1, 0, st));
+  return BVG_OK;
+}
+
+struct GenWs {
+  void *A, *Y, *T1, *T2, *XS;
+  float* cond[9];
+  float* spk;
+  EcapaWs e;
+  float *latent_dev, *mel_dev, *wav_dev;
+  int16_t* pcm_dev;
+};
+
+void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
+  const size_t es = dtype_size(dtype);
+  int64_t maxel = (int64_t)P->C[0] * T0;
+  int64_t T = T0;
+  for (int i = 0; i < P->n_stage; ++i) {
+    T *= P->cfg.upsample_rates[i];
+    maxel = std::max<int64_t>(maxel, (int64_t)P->C[i + 1] * T);
+  }
+  const size_t bytes = (size_t)B * maxel * es;
+  g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
+  for (int i = 0; i <= P->n_stage; ++i) g->cond[i] = b.takef(Bm * P->C[i]);
+  g->spk = b.takef(Bm * P->cfg.speaker_embedding_dim);
+  carve_ecapa(b, Bm, Tm, &g->e);
+  // staging for the host-buffer entry point
+  g->latent_dev = b.takef(B * T0 * P->cfg.gpt_dim);
+  g->mel_dev = b.takef(Bm * Tm * P->cfg.num_mels);
+  g->wav_dev = b.takef(B * T0 * P->total_up);
+  g->pcm_dev = static_cast<int16_t*>(b.take((size_t)B * T0 * P->total_up * 2));
+}
+
+int act_launch(void* dst, const void* src, const float* a, const float* b_, int64_t B, int64_t Cn, int64_t T,
+               int dtype, cudaStream_t st) {
+  return act1d_launch(dst, src, a, b_, B, Cn, T, dtype, /*precise=*/dtype == BVG_F32 ? 1 : 0, st);
+}
+
+int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, int64_t B, int64_t T, int dil,
+             int dtype, cudaStream_t st) {
+  ep.bias = L.bias;
+  return conv1d_simt_launch(dst, (int64_t)L.Cout * T, src, nullptr, (int64_t)L.Cin * T, T, 1, L.w, ep, B, L.Cin,
+                            L.Cout, T, L.K, dil, 0, dtype, dtype, st);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* bvg_last_error(void) { return g_error.c_str(); }
+const char* bvg_version(void) { return "bigvgan_b200 0.1 sm_100a"; }
+int64_t bvg_launch_count(void) { return g_launches; }
+void bvg_launch_count_reset(void) { g_launches = 0; }
+
+void bvg_profile_begin(void) {
+  g_prof_on = true;
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof_recs.clear();
+}
+
+int bvg_profile_end(float* ms_per_class, int64_t* launches_per_class) {
+  g_prof_on = false;
+  for (int i = 0; i < KC_COUNT; ++i) { if (ms_per_class) ms_per_class[i] = 0.f; if (launches_per_class) launches_per_class[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    BVG_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    BVG_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (ms_per_class) ms_per_class[r.kc] += ms;
+    if (launches_per_class) launches_per_class[r.kc] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  return BVG_OK;
+}
+
+int bvg_act1d_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                  const float* up_taps_host, const float* down_taps_host, int64_t B, int64_t C, int64_t T, int dtype,
+                  int precise, void* stream) {
+  static const float ref[12] = {BVG_F0, BVG_F1, BVG_F2, BVG_F3, BVG_F4, BVG_F5,
+                                BVG_F5, BVG_F4, BVG_F3, BVG_F2, BVG_F1, BVG_F0};
+  for (const float* taps : {up_taps_host, down_taps_host})
+    if (taps)
+      for (int i = 0; i < 12; ++i)
+        BVG_CHECK_ARG(fabsf(taps[i] - ref[i]) <= 1e-6f,
+                      "act1d: filter tap %d = %g differs from the built-in kaiser-sinc tap %g (the fused kernel "
+                      "hard-codes filter 12 / ratio 2, like the reference's)", i, taps[i], ref[i]);
+  return act1d_launch(dst, src, alpha_log, beta_log, B, C, T, dtype, precise, (cudaStream_t)stream);
+}
+
+int bvg_conv1d_fwd(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
+                   const void* res2, float scale, int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation,
+                   int reflect_pad, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(weight && Cin > 0 && Cout > 0 && K > 0, "conv1d: bad weight");
+  float* wk = nullptr;   // layer-level test entry point: a temporary repack buffer is acceptable here
+  BVG_CUDA(cudaMallocAsync((void**)&wk, (size_t)Cin * Cout * K * 4, st));
+  int rc = repack_conv_weight_launch(wk, weight, Cout, Cin, K, 0, st);
+  if (rc == BVG_OK) {
+    ConvEpilogue ep;
+    ep.bias = bias; ep.res1 = res1; ep.res2 = res2; ep.scale = scale;
+    rc = conv1d_simt_launch(dst, Cout * T, src, nullptr, Cin * T, T, 1, wk, ep, B, Cin, Cout, T, K, dilation,
+                            reflect_pad ? 1 : 0, dtype, dtype, st);
+  }
+  cudaFreeAsync(wk, st);
+  return rc;
+}
+
+int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, const float* bias, const float* cond,
+                     int64_t Bc, int64_t B, int64_t Cin, int64_t Cout, int64_t Tin, int K, int stride, int dtype,
+                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(weight && Cin > 0 && Cout > 0 && K > 0, "convtr1d: bad weight");
+  BVG_CHECK_ARG(!cond || Bc == 1 || Bc == B, "convtr1d: cond batch must be 1 or B");
+  float* wk = nullptr;
+  BVG_CUDA(cudaMallocAsync((void**)&wk, (size_t)Cin * Cout * K * 4, st));
+  int rc = repack_conv_weight_launch(wk, weight, Cout, Cin, K, 1, st);
+  if (rc == BVG_OK) {
+    ConvEpilogue ep;
+    ep.bias = bias; ep.cond = cond; ep.cond_B = Bc;
+    rc = convtr1d_simt_launch(dst, src, wk, ep, B, Cin, Cout, Tin, K, stride, dtype, st);
+  }
+  cudaFreeAsync(wk, st);
+  return rc;
+}
+
+int bvg_plan_create(bvg_plan** out, const bvg_config* cfg) {
+  BVG_CHECK_ARG(out && cfg, "plan_create: null argument");
+  BVG_CHECK_ARG(cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8, "plan_create: num_upsamples out of range");
+  BVG_CHECK_ARG(cfg->num_kernels >= 1 && cfg->num_kernels <= 4, "plan_create: num_kernels out of range");
+  BVG_CHECK_ARG(cfg->gpt_dim > 0 && cfg->upsample_initial_channel > 0 && cfg->speaker_embedding_dim > 0 &&
+                    cfg->num_mels > 0, "plan_create: non-positive dimension");
+  BVG_CHECK_ARG((cfg->upsample_initial_channel >> cfg->num_upsamples) >= 1,
+                "plan_create: upsample_initial_channel too small for %d stages", cfg->num_upsamples);
+  int ndev = 0;
+  BVG_CUDA(cudaGetDeviceCount(&ndev));
+  BVG_CHECK_ARG(cfg->device >= 0 && cfg->device < ndev, "plan_create: no CUDA device %d", cfg->device);
+  cudaDeviceProp prop;
+  BVG_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  BVG_CHECK_ARG(prop.major == 10, "plan_create: this library is built for sm_100a only (device is sm_%d%d)",
+                prop.major, prop.minor);
+  bvg_plan* P = new bvg_plan();
+  P->cfg = *cfg;
+  P->n_stage = cfg->num_upsamples;
+  P->C[0] = cfg->upsample_initial_channel;
+  for (int i = 0; i < P->n_stage; ++i) {
+    P->C[i + 1] = cfg->upsample_initial_channel >> (i + 1);
+    P->total_up *= cfg->upsample_rates[i];
+  }
+  *out = P;
+  return BVG_OK;
+}
+
+void bvg_plan_destroy(bvg_plan* P) {
+  if (!P) return;
+  cudaSetDevice(P->cfg.device);
+  for (void* p : P->allocs) cudaFree(p);
+  delete P;
+}
+
+int bvg_plan_set_tensor(bvg_plan* P, const char* key, const float* data, int64_t numel) {
+  BVG_CHECK_ARG(P && key && (data || numel == 0) && numel >= 0, "plan_set_tensor: bad argument");
+  if (P->finalized) { set_error("plan_set_tensor: plan already finalised"); return BVG_ERR_STATE; }
+  P->host[key].assign(data, data + numel);
+  return BVG_OK;
+}
+
+int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
+  BVG_CHECK_ARG(P, "plan_finalize: null plan");
+  if (P->finalized) return BVG_OK;
+  (void)enable_bf16_umma;
+  BVG_CUDA(cudaSetDevice(P->cfg.device));
+  const bvg_config& c = P->cfg;
+  const int E = c.speaker_embedding_dim;
+  BVG_TRY(make_conv(P, "conv_pre.weight", "conv_pre.bias", P->C[0], c.gpt_dim, 7, false, &P->conv_pre));
+  BVG_TRY(make_conv(P, "cond_layer.weight", "cond_layer.bias", P->C[0], E, 1, false, &P->cond_layer));
+  P->ups.resize(P->n_stage);
+  P->conds.resize(P->n_stage);
+  for (int i = 0; i < P->n_stage; ++i) {
+    const std::string u = "ups." + std::to_string(i) + ".0";
+    BVG_TRY(make_conv(P, u + ".weight", u + ".bias", P->C[i + 1], P->C[i], c.upsample_kernel_sizes[i], true, &P->ups[i]));
+    if (c.cond_in_each_up_layer) {
+      const std::string k = "conds." + std::to_string(i);
+      BVG_TRY(make_conv(P, k + ".weight", k + ".bias", P->C[i + 1], E, 1, false, &P->conds[i]));
+    }
+  }
+  P->res.resize((size_t)P->n_stage * c.num_kernels);
+  for (int i = 0; i < P->n_stage; ++i)
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const int n = i * c.num_kernels + j;
+      ResBlock& R = P->res[n];
+      R.K = c.resblock_kernel_sizes[j];
+      const int ch = P->C[i + 1];
+      const std::string p = "resblocks." + std::to_string(n);
+      for (int m = 0; m < 3; ++m) {
+        R.dil[m] = c.resblock_dilation_sizes[j][m];
+        const std::string a = p + ".convs1." + std::to_string(m), b = p + ".convs2." + std::to_string(m);
+        BVG_TRY(make_conv(P, a + ".weight", a + ".bias", ch, ch, R.K, false, &R.c1[m]));
+        BVG_TRY(make_conv(P, b + ".weight", b + ".bias", ch, ch, R.K, false, &R.c2[m]));
+      }
+      for (int m = 0; m < 6; ++m)
+        BVG_TRY(make_act(P, p + ".activations." + std::to_string(m), ch, &R.alpha[m], &R.beta[m]));
+    }
+  const int chp = P->C[P->n_stage];
+  BVG_TRY(make_act(P, "activation_post", chp, &P->post_alpha, &P->post_beta));
+  BVG_TRY(upload_key(P, "conv_post.weight", (int64_t)chp * 7, &P->post_w));   // [1,Cin,7] == [Cin][7]
+  BVG_TRY(upload_key(P, "conv_post.bias", 1, &P->post_bias));
+  // speaker encoder
+  const std::string S = "speaker_encoder.";
+  BVG_TRY(make_tdnn(P, S + "blocks.0", c.num_mels, kEC, 5, 1, &P->e_block0));
+  for (int i = 0; i < 3; ++i) {
+    const std::string b = S + "blocks." + std::to_string(i + 1);
+    SERes2& R = P->e_blk[i];
+    BVG_TRY(make_tdnn(P, b + ".tdnn1", kEC, kEC, 1, 1, &R.tdnn1));
+    for (int j = 0; j < 7; ++j)
+      BVG_TRY(make_tdnn(P, b + ".res2net_block.blocks." + std::to_string(j), kEC / 8, kEC / 8, 3, i + 2, &R.r2n[j]));
+    BVG_TRY(make_tdnn(P, b + ".tdnn2", kEC, kEC, 1, 1, &R.tdnn2));
+    BVG_TRY(make_conv(P, b + ".se_block.conv1.conv.weight", b + ".se_block.conv1.conv.bias", kEA, kEC, 1, false, &R.se1));
+    BVG_TRY(make_conv(P, b + ".se_block.conv2.conv.weight", b + ".se_block.conv2.conv.bias", kEC, kEA, 1, false, &R.se2));
+  }
+  BVG_TRY(make_tdnn(P, S + "mfa", kEM, kEM, 1, 1, &P->e_mfa));
+  // asp.tdnn over cat([x, mean, std]) (4608 ch): x part keeps ReLU+BN, the (mean,std) part becomes a
+  // per-utterance additive term that also carries the conv bias
+  BVG_TRY(make_tdnn(P, S + "asp.tdnn", 3 * kEM, kEA, 1, 1, &P->e_asp_tdnn, 0, kEM));
+  BVG_TRY(make_conv(P, S + "asp.tdnn.conv.conv.weight", "", kEA, 3 * kEM, 1, false, &P->e_asp_ctx, kEM, 3 * kEM));
+  P->e_asp_ctx.bias = P->e_asp_tdnn.conv.bias;
+  P->e_asp_tdnn.conv.bias = nullptr;
+  BVG_TRY(make_conv(P, S + "asp.conv.conv.weight", S + "asp.conv.conv.bias", kEM, kEA, 1, false, &P->e_asp_conv));
+  BVG_TRY(make_bn(P, S + "asp_bn.norm", 2 * kEM, &P->asp_bn_scale, &P->asp_bn_shift));
+  BVG_TRY(make_conv(P, S + "fc.conv.weight", S + "fc.conv.bias", E, 2 * kEM, 1, false, &P->e_fc));
+  BVG_CUDA(cudaDeviceSynchronize());
+  P->host.clear();
+  P->finalized = true;
+  return BVG_OK;
+}
+
+size_t bvg_workspace_bytes(const bvg_plan* P, int64_t B, int64_t T0, int64_t Tm, int dtype) {
+  if (!P || B <= 0 || T0 <= 0) return 0;
+  Bump b(nullptr, ~size_t(0));
+  GenWs g;
+  // sized for per-utterance reference mels (Bm == B); a broadcast mel needs less
+  carve_gen(P, b, B, T0, B, std::max<int64_t>(Tm, 1), dtype, &g);
+  return b.off + 256;
+}
+
+int bvg_speaker_embed(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, float* spk, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  BVG_CHECK_ARG(P && mel && spk && workspace, "speaker_embed: null argument");
+  if (!P->finalized) { set_error("speaker_embed: plan not finalised"); return BVG_ERR_STATE; }
+  Bump b(workspace, workspace_bytes);
+  EcapaWs w;
+  carve_ecapa(b, Bm, Tm, &w);
+  if (b.overflow) { set_error("speaker_embed: workspace too small (%zu < %zu)", workspace_bytes, b.off); return BVG_ERR_WORKSPACE; }
+  return ecapa_forward(P, mel, Bm, Tm, spk, w, (cudaStream_t)stream);
+}
+
+int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const float* spk_in, int64_t B, int64_t T0,
+               int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(P && latent && workspace, "decode: null argument");
+  if (!P->finalized) { set_error("decode: plan not finalised"); return BVG_ERR_STATE; }
+  BVG_CHECK_ARG((mel != nullptr) != (spk_in != nullptr), "decode: pass exactly one of mel / spk");
+  BVG_CHECK_ARG(dtype == BVG_F32 || dtype == BVG_BF16, "decode: dtype must be BVG_F32 or BVG_BF16");
+  BVG_CHECK_ARG(B >= 1 && T0 >= 1, "decode: empty batch or zero latent frames (B=%lld T0=%lld)", (long long)B, (long long)T0);
+  // models.py:205-209: Bm == 2B enters a training-only branch that references an undefined attribute
+  BVG_CHECK_ARG(Bm == 1 || Bm == B, "decode: reference mel batch must be 1 or B (got %lld for B=%lld)", (long long)Bm, (long long)B);
+  BVG_CHECK_ARG(t_lo_pad >= 0 && t_hi_pad >= 0 && t_lo_pad + t_hi_pad < T0, "decode: bad halo");
+  BVG_CHECK_ARG(wav || pcm16, "decode: no output buffer");
+  const bvg_config& c = P->cfg;
+  Bump bump(workspace, workspace_bytes);
+  GenWs g;
+  carve_gen(P, bump, B, T0, Bm, mel ? Tm : 1, dtype, &g);
+  if (bump.overflow) {
+    set_error("decode: workspace too small (%zu bytes given, %zu needed)", workspace_bytes, bump.off);
+    return BVG_ERR_WORKSPACE;
+  }
+  const int E = c.speaker_embedding_dim;
+  const float* spk = spk_in;
+  if (mel) {
+    BVG_TRY(ecapa_forward(P, mel, Bm, Tm, g.spk, g.e, st));
+    spk = g.spk;
+  }
+  // speaker conditioning vectors cond_layer(spk), conds[i](spk)  (models.py:226, :233-234): [Bm, C]
+  {
+    ConvEpilogue ep;
+    BVG_TRY(conv_f32(g.cond[0], P->C[0], spk, nullptr, E, 1, 1, P->cond_layer, ep, Bm, 1, 1, 0, st));
+    if (c.cond_in_each_up_layer)
+      for (int i = 0; i < P->n_stage; ++i)
+        BVG_TRY(conv_f32(g.cond[i + 1], P->C[i + 1], spk, nullptr, E, 1, 1, P->conds[i], ep, Bm, 1, 1, 0, st));
+  }
+  // conv_pre on latent^T (models.py:220-226): read [B,T0,gpt_dim] through strides
+  {
+    ConvEpilogue ep;
+    ep.bias = P->conv_pre.bias; ep.cond = g.cond[0]; ep.cond_B = Bm;
+    BVG_TRY(conv1d_simt_launch(g.XS, (int64_t)P->C[0] * T0, latent, nullptr, T0 * c.gpt_dim, 1, c.gpt_dim,
+                               P->conv_pre.w, ep, B, c.gpt_dim, P->C[0], T0, 7, 1, 0, BVG_F32, dtype, st));
+  }
+  int64_t T = T0;
+  const float inv_nk = 1.0f / (float)c.num_kernels;
+  for (int i = 0; i < P->n_stage; ++i) {
+    const int u = c.upsample_rates[i];
+    const int ch = P->C[i + 1];
+    {
+      ConvEpilogue ep;
+      ep.bias = P->ups[i].bias;
+      if (c.cond_in_each_up_layer) { ep.cond = g.cond[i + 1]; ep.cond_B = Bm; }
+      BVG_TRY(convtr1d_simt_launch(g.A, g.XS, P->ups[i].w, ep, B, P->C[i], ch, T, P->ups[i].K, u, dtype, st));
+    }
+    T *= u;
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
+      const void* y = g.A;                       // AMPBlock1.forward models.py:65-74
+      for (int m = 0; m < 3; ++m) {
+        BVG_TRY(act_launch(g.T1, y, R.alpha[2 * m], R.beta[2 * m], B, ch, T, dtype, st));
+        ConvEpilogue e1;
+        BVG_TRY(gen_conv(g.T2, g.T1, R.c1[m], e1, B, T, R.dil[m], dtype, st));
+        BVG_TRY(act_launch(g.T1, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, ch, T, dtype, st));
+        ConvEpilogue e2;
+        e2.res1 = y;                              // x = xt + x
+        if (m < 2) {
+          BVG_TRY(gen_conv(g.Y, g.T1, R.c2[m], e2, B, T, 1, dtype, st));
+          y = g.Y;
+        } else {                                  // xs += block(x); x = xs / num_kernels (models.py:237-243)
+          if (j > 0) e2.res2 = g.XS;
+          if (j == c.num_kernels - 1) e2.scale = inv_nk;
+          BVG_TRY(gen_conv(g.XS, g.T1, R.c2[m], e2, B, T, 1, dtype, st));
+        }
+      }
+    }
+  }
+  const int chp = P->C[P->n_stage];
+  BVG_TRY(act_launch(g.T1, g.XS, P->post_alpha, P->post_beta, B, chp, T, dtype, st));
+  BVG_TRY(conv_post_launch(wav, pcm16, g.T1, P->post_w, P->post_bias, B, chp, T, 7, t_lo_pad * P->total_up,
+                           t_hi_pad * P->total_up, dtype, st));
+  return BVG_OK;
+}
+
+int bvg_decode_host(const bvg_plan* P, const float* latent_host, const float* mel_host, int64_t B, int64_t T0,
+                    int64_t Bm, int64_t Tm, int dtype, float* wav_host, int16_t* pcm16_host, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(P && latent_host && mel_host && workspace && (wav_host || pcm16_host), "decode_host: null argument");
+  BVG_CHECK_ARG(B >= 1 && T0 >= 1 && Tm >= 1 && (Bm == 1 || Bm == B), "decode_host: bad shape");
+  Bump bump(workspace, workspace_bytes);
+  GenWs g;
+  carve_gen(P, bump, B, T0, Bm, Tm, dtype, &g);
+  if (bump.overflow) { set_error("decode_host: workspace too small (%zu < %zu)", workspace_bytes, bump.off); return BVG_ERR_WORKSPACE; }
+  const int64_t L = T0 * P->total_up;
+  BVG_CUDA(cudaMemcpyAsync(g.latent_dev, latent_host, (size_t)B * T0 * P->cfg.gpt_dim * 4, cudaMemcpyHostToDevice, st));
+  BVG_CUDA(cudaMemcpyAsync(g.mel_dev, mel_host, (size_t)Bm * Tm * P->cfg.num_mels * 4, cudaMemcpyHostToDevice, st));
+  BVG_TRY(bvg_decode(P, g.latent_dev, g.mel_dev, nullptr, B, T0, Bm, Tm, dtype, wav_host ? g.wav_dev : nullptr,
+                     pcm16_host ? g.pcm_dev : nullptr, 0, 0, workspace, workspace_bytes, stream));
+  if (wav_host) BVG_CUDA(cudaMemcpyAsync(wav_host, g.wav_dev, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
+  if (pcm16_host) BVG_CUDA(cudaMemcpyAsync(pcm16_host, g.pcm_dev, (size_t)B * L * 2, cudaMemcpyDeviceToHost, st));
+  BVG_CUDA(cudaStreamSynchronize(st));
+  return BVG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated
+golden fixtures.  All tests here need a B200: run with `pytest -m gpu`."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_GATE = 1e-4          # BASELINE.json north_star: fp32 path max-abs waveform error <= 1e-4
+BF16_SNR_GATE = 40.0      # bf16 path waveform SNR >= 40 dB
+
+
+@pytest.fixture(scope="module")
+def P():
+    import index_tts_ipex_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return pkg
+
+
+def _cfg(name):
+    return O.small_config() if str(name) == "small" else O.indextts15_config()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+_models = {}
+
+
+def _model(P, cfg_name, wseed, mode):
+    key = (cfg_name, wseed, mode)
+    if key not in _models:
+        h = _cfg(cfg_name)
+        sd = O.make_state_dict(h, wseed, mode)
+        m = P.BigVGAN(h, use_cuda_kernel=True)
+        m.load_state_dict(sd, strict=True)
+        m = m.to("cuda").eval()
+        m.remove_weight_norm()
+        _models[key] = (m, sd, h)
+    return _models[key]
+
+
+# ------------------------------------------------------------------------------------ Activation1d
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 6, 11, 12, 13, 31, 32, 33, 100, 257, 1000, 4095, 4096, 4097])
+def test_act1d_fp32_vs_reference_golden(P, golden_dir, T):
+    g = _load(golden_dir, "act1d_cases")
+    x = torch.from_numpy(g[f"T{T}.x"]).cuda()
+    a = torch.from_numpy(g[f"T{T}.alpha"]).cuda()
+    b = torch.from_numpy(g[f"T{T}.beta"]).cuda()
+    filt = torch.from_numpy(g[f"T{T}.filt"]).view(1, 1, 12)
+    y = P.anti_alias_activation_forward(x, filt, filt, a, b)
+    assert y.shape == x.shape and y.dtype == x.dtype
+    np.testing.assert_allclose(y.cpu().numpy(), g[f"T{T}.y"], rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T", [7, 64, 1000, 4104])
+def test_act1d_half_precisions(P, dtype, T):
+    gen = torch.Generator().manual_seed(T)
+    x = (torch.randn(3, 10, T, generator=gen) * 1.5).to(dtype)
+    a = torch.randn(10, generator=gen) * 0.5
+    b = torch.randn(10, generator=gen) * 0.5
+    ref = O.act1d(x.double(), a.double(), b.double())
+    y = P.anti_alias_activation_forward(x.cuda(), None, None, a.cuda(), b.cuda())
+    assert y.dtype == dtype
+    err = (y.double().cpu() - ref).abs()
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    # output rounding (half ulp of |ref|) plus fast-math slack
+    assert float((err - (ref.abs() * eps * 0.5 + 2e-3)).max()) <= 0, float(err.max())
+    # the fast (MUFU) path with fp32 I/O stays within 2e-5 of the oracle
+    xf = x.float()
+    yf = P.anti_alias_activation_forward(xf.cuda(), None, None, a.cuda(), b.cuda(), precise=False)
+    assert float((yf.double().cpu() - ref).abs().max()) < 2e-5
+
+
+def test_act1d_large_rows_and_linearity_property(P):
+    """Size-independent property at a full-size shape: with beta -> +inf the snake term vanishes and
+    Activation1d is the linear up/down filter pair, whose DC gain is exactly 1 (taps sum to 1)."""
+    B, Cn, T = 4, 96, 60160          # stage-3 shape of a 10 s utterance (T0=235)
+    x = torch.full((B, Cn, T), 0.75, device="cuda")
+    a = torch.zeros(Cn, device="cuda")
+    b = torch.full((Cn,), 60.0, device="cuda")     # 1/(e^60) ~ 0
+    y = P.anti_alias_activation_forward(x, None, None, a, b)
+    assert float((y - 0.75).abs().max()) < 1e-6
+
+
+def test_act1d_rejects_bad_input(P):
+    x = torch.randn(1, 4, 16)
+    with pytest.raises(RuntimeError):
+        P.anti_alias_activation_forward(x, None, None, torch.zeros(4), torch.zeros(4))       # CPU tensor
+    with pytest.raises(RuntimeError):
+        P.anti_alias_activation_forward(x.cuda(), torch.ones(1, 1, 12), None, torch.zeros(4).cuda(), torch.zeros(4).cuda())
+    with pytest.raises(RuntimeError):
+        P.anti_alias_activation_forward(x.cuda().double(), None, None, torch.zeros(4).cuda(), torch.zeros(4).cuda())
+
+
+# ------------------------------------------------------------------------------------ conv layers
+def _conv1d(P, x, w, b, dil, reflect=False, res1=None, res2=None, scale=1.0):
+    L = P.capi.lib()
+    B, Cin, T = x.shape
+    Cout, _, K = w.shape
+    y = torch.empty(B, Cout, T, device="cuda", dtype=x.dtype)
+    P.capi.check(L.bvg_conv1d_fwd(y.data_ptr(), x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                  res1.data_ptr() if res1 is not None else None,
+                                  res2.data_ptr() if res2 is not None else None, scale, B, Cin, Cout, T, K, dil,
+                                  int(reflect), P.capi.dtype_code(x.dtype), torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+@pytest.mark.parametrize("Cin,Cout,T,K,dil", [(96, 96, 37, 3, 1), (96, 96, 300, 11, 5), (24, 24, 1000, 7, 3),
+                                               (40, 192, 13, 7, 1), (130, 129, 129, 3, 1), (7, 5, 1, 1, 1)])
+def test_conv1d_vs_torch(P, Cin, Cout, T, K, dil):
+    gen = torch.Generator().manual_seed(Cin * 31 + T)
+    x = torch.randn(2, Cin, T, generator=gen)
+    w = torch.randn(Cout, Cin, K, generator=gen) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=gen)
+    r1 = torch.randn(2, Cout, T, generator=gen)
+    r2 = torch.randn(2, Cout, T, generator=gen)
+    ref = (torch.nn.functional.conv1d(x.double(), w.double(), b.double(), dilation=dil, padding=dil * (K - 1) // 2)
+           + r1.double() + r2.double()) / 3
+    y = _conv1d(P, x.cuda(), w.cuda(), b.cuda(), dil, res1=r1.cuda(), res2=r2.cuda(), scale=1.0 / 3)
+    assert float((y.double().cpu() - ref).abs().max()) < 2e-5
+    if T > dil * (K - 1) // 2:
+        ref = torch.nn.functional.conv1d(
+            torch.nn.functional.pad(x.double(), (dil * (K - 1) // 2,) * 2, mode="reflect") if K > 1 else x.double(),
+            w.double(), b.double(), dilation=dil)
+        y = _conv1d(P, x.cuda(), w.cuda(), b.cuda(), dil, reflect=True)
+        assert float((y.double().cpu() - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,Tin,K,u", [(192, 96, 9, 8, 4), (12, 6, 21, 4, 2), (48, 24, 300, 4, 4), (33, 17, 70, 8, 4)])
+def test_convtr1d_vs_torch(P, Cin, Cout, Tin, K, u):
+    gen = torch.Generator().manual_seed(Cin + Tin)
+    x = torch.randn(3, Cin, Tin, generator=gen)
+    w = torch.randn(Cin, Cout, K, generator=gen) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=gen)
+    cond = torch.randn(3, Cout, generator=gen)
+    ref = torch.nn.functional.conv_transpose1d(x.double(), w.double(), b.double(), stride=u, padding=(K - u) // 2) \
+        + cond.double().unsqueeze(-1)
+    L = P.capi.lib()
+    xd, wd, bd, cd = x.cuda(), w.cuda(), b.cuda(), cond.cuda()
+    y = torch.empty(3, Cout, Tin * u, device="cuda")
+    P.capi.check(L.bvg_convtr1d_fwd(y.data_ptr(), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), cd.data_ptr(), 3,
+                                    3, Cin, Cout, Tin, K, u, 0, torch.cuda.current_stream().cuda_stream))
+    assert float((y.double().cpu() - ref).abs().max()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------ speaker encoder
+def test_speaker_encoder_vs_reference_golden(P, golden_dir):
+    g = _load(golden_dir, "layer_cases")
+    m, sd, h = _model(P, "small", 11, "wild")
+    assert O.state_dict_digest(sd) == str(g["digest"])
+    spk = m.speaker_embed(torch.from_numpy(g["ecapa_mel"]).cuda())
+    np.testing.assert_allclose(spk.cpu().numpy(), g["ecapa_y"], rtol=0, atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------ whole path
+@pytest.mark.parametrize("name", ["full15_tame_T12", "full15_wild_T9", "small_wild_T17_bcast", "small_tame_T1"])
+def test_full_forward_fp32_vs_reference_golden(P, golden_dir, name):
+    g = _load(golden_dir, name)
+    m, sd, h = _model(P, str(g["config"]), int(g["wseed"]), str(g["mode"]))
+    assert O.state_dict_digest(sd) == str(g["digest"])
+    latent, mel = O.synthetic_inputs(h, int(g["B"]), int(g["T0"]), int(g["Tm"]), seed=int(g["iseed"]), Bm=int(g["Bm"]))
+    wav, none = m(latent.cuda(), mel.cuda())
+    assert none is None
+    assert tuple(wav.shape) == g["wav"].shape and wav.dtype == torch.float32
+    spk = m.speaker_embed(mel.cuda())
+    np.testing.assert_allclose(spk.cpu().numpy(), g["spk"], rtol=0, atol=5e-5)
+    err = float(np.abs(wav.cpu().numpy() - g["wav"]).max())
+    assert err <= FP32_GATE, err
+    assert err <= 2e-5, f"fp32 path drifted: {err}"     # far inside the gate in practice
+
+
+@pytest.mark.parametrize("name", ["full15_tame_T12", "full15_wild_T9", "small_wild_T17_bcast"])
+def test_full_forward_bf16_snr_vs_reference_golden(P, golden_dir, name):
+    g = _load(golden_dir, name)
+    m, sd, h = _model(P, str(g["config"]), int(g["wseed"]), str(g["mode"]))
+    latent, mel = O.synthetic_inputs(h, int(g["B"]), int(g["T0"]), int(g["Tm"]), seed=int(g["iseed"]), Bm=int(g["Bm"]))
+    m.precision = "bf16"
+    try:
+        wav = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    finally:
+        m.precision = None
+    snr = O.snr_db(torch.from_numpy(g["wav"]), wav.cpu())
+    assert snr >= BF16_SNR_GATE, snr
+
+
+def test_full_size_10s_fp32_vs_oracle(P):
+    """BASELINE config 2: B=1, T0=235 (10.03 s), fp32, max-abs <= 1e-4 against the oracle (run on the
+    GPU box through PyTorch fp32 with TF32 off; the oracle itself is pinned to the reference by
+    tests/test_oracle_golden.py)."""
+    m, sd, h = _model(P, "indextts15", 0, "tame")
+    latent, mel = O.synthetic_inputs(h, 1, 235, 281, seed=1)
+    wav, _ = m(latent.cuda(), mel.cuda())
+    assert tuple(wav.shape) == (1, 1, 240640)
+    sdc = {k: v.cuda() for k, v in O.fold_weight_norm(sd).items()}
+    with torch.no_grad():
+        ref = O.bigvgan_forward(latent.cuda(), mel.cuda(), sdc, h)
+    err = float((wav - ref).abs().max())
+    assert err <= FP32_GATE, err
+    assert float(ref.abs().max()) > 0.05      # non-degenerate output
+
+
+def test_batch32_bf16_snr_and_batch_independence(P):
+    """BASELINE config 3 shape (B=32 x 10 s, bf16), SNR >= 40 dB vs the fp32 oracle on 2 of the 32
+    utterances, plus the size-independent property that utterances do not interact: decoding a
+    sub-batch gives bit-identical waveforms."""
+    m, sd, h = _model(P, "indextts15", 0, "tame")
+    latent, mel = O.synthetic_inputs(h, 32, 235, 281, seed=2)
+    m.precision = "bf16"
+    try:
+        wav = m.decode(latent.cuda(), mel_ref=mel.cuda())
+        sub = m.decode(latent[5:7].cuda(), mel_ref=mel[5:7].cuda())
+    finally:
+        m.precision = None
+    assert tuple(wav.shape) == (32, 1, 240640)
+    assert torch.equal(wav[5:7], sub)
+    sdc = {k: v.cuda() for k, v in O.fold_weight_norm(sd).items()}
+    with torch.no_grad():
+        ref = O.bigvgan_forward(latent[5:7].cuda(), mel[5:7].cuda(), sdc, h)
+    snr = O.snr_db(ref.cpu(), sub.cpu())
+    assert snr >= BF16_SNR_GATE, snr
+
+
+def test_mel_broadcast_equals_repeated(P):
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 3, 10, 30, seed=9, Bm=1)
+    a, _ = m(latent.cuda(), mel.cuda())
+    b, _ = m(latent.cuda(), mel.expand(3, -1, -1).contiguous().cuda())
+    assert torch.equal(a, b)
+
+
+def test_long_form_chunked_equals_unchunked(P):
+    """BASELINE config 5a: overlapped chunks with a 36-frame halo reproduce the unchunked decode
+    (finite receptive field <= 35 frames/side)."""
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 2, 300, 40, seed=4, Bm=1)
+    full, _ = m(latent.cuda(), mel.cuda())
+    chunked = m.decode_long(latent.cuda(), mel.cuda(), chunk_frames=64, halo_frames=36)
+    assert chunked.shape == full.shape
+    assert float((chunked - full).abs().max()) <= 1e-6
+    short = m.decode_long(latent.cuda(), mel.cuda(), chunk_frames=64, halo_frames=4)
+    assert float((short - full).abs().max()) > 1e-6     # the halo is what makes it exact
+
+
+def test_long_form_60s_full_config(P):
+    """60 s utterance (T0=1407) of the IndexTTS-1.5 generator: chunked == unchunked within the fp32 gate."""
+    m, sd, h = _model(P, "indextts15", 0, "tame")
+    latent, mel = O.synthetic_inputs(h, 1, 1407, 281, seed=6)
+    full, _ = m(latent.cuda(), mel.cuda())
+    chunked = m.decode_long(latent.cuda(), mel.cuda(), chunk_frames=256, halo_frames=36)
+    assert tuple(full.shape) == (1, 1, 1407 * 1024)
+    assert float((chunked - full).abs().max()) <= 1e-5
+
+
+def test_pcm16_epilogue(P):
+    """infer.py:206-212,234: clamp(32767*wav, +-32767) -> int16."""
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 2, 9, 30, seed=3)
+    wav = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    pcm = m.decode(latent.cuda(), mel_ref=mel.cuda(), pcm16=True)
+    ref = torch.clamp(32767 * wav.squeeze(1), -32767.0, 32767.0).type(torch.int16)
+    assert pcm.dtype == torch.int16 and torch.equal(pcm, ref)
+
+
+def test_host_entry_point_matches_device_call(P):
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 2, 9, 30, seed=3)
+    dev = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    host = m.decode_host(latent.pin_memory(), mel.pin_memory(), "cuda:0")
+    assert host.device.type == "cpu" and torch.equal(host, dev.cpu())
+
+
+def test_autocast_contract(P):
+    """infer.py:194,496 call the vocoder under torch.autocast(fp16): output takes the autocast dtype."""
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 1, 6, 30, seed=8)
+    ref, _ = m(latent.cuda(), mel.cuda())
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        wav, none = m(latent.cuda(), mel.cuda())
+    assert none is None and wav.dtype == torch.float16
+    assert O.snr_db(ref.cpu(), wav.float().cpu()) >= 35.0
+
+
+def test_error_behaviour(P):
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 2, 6, 30, seed=8)
+    with pytest.raises(RuntimeError):
+        m(latent, mel)                                        # CPU tensors: no CPU path
+    with pytest.raises(RuntimeError):
+        m(latent.cuda(), torch.cat([mel, mel]).cuda())         # B' == 2B: training-only branch (models.py:205-209)
+    with pytest.raises(RuntimeError):
+        m(latent.cuda()[..., :5], mel.cuda())                  # wrong gpt_dim
+    with pytest.raises(RuntimeError):
+        m(latent.cuda(), mel.cuda()[:, :3])                    # too few mel frames for reflect padding
+    with pytest.raises(NotImplementedError):
+        m(latent.cuda(), mel.cuda(), lens=torch.ones(2))
