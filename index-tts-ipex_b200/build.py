@@ -31,14 +31,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libbigvgan_b200 needs the CUDA toolkit to build")
 
 
-def _stale() -> bool:
-    out = lib_path()
-    if not os.path.exists(out):
-        return True
-    t = os.path.getmtime(out)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+def _src_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
         os.path.join(os.path.dirname(HERE), "include", "bigvgan_b200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def _stale() -> bool:
+    # content hash, not mtimes: the tree is copied to the GPU box and mtimes need not survive
+    out = lib_path()
+    stamp = out + ".srchash"
+    if not os.path.exists(out) or not os.path.exists(stamp):
+        return True
+    return open(stamp).read().strip() != _src_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -69,6 +79,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(tmp, lib_path())
+    with open(lib_path() + ".srchash", "w") as f:
+        f.write(_src_hash())
     return lib_path()
 
 
