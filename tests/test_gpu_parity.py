@@ -73,8 +73,8 @@ def test_act1d_half_precisions(P, dtype, T):
     assert y.dtype == dtype
     err = (y.double().cpu() - ref).abs()
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
-    # output rounding (half ulp of |ref|) plus fast-math slack
-    assert float((err - (ref.abs() * eps * 0.5 + 2e-3)).max()) <= 0, float(err.max())
+    # output rounding (half an ulp is at most eps*|ref|) plus fast-math slack
+    assert float((err - (ref.abs() * eps + 2e-3)).max()) <= 0, float(err.max())
     # the fast (MUFU) path with fp32 I/O stays within 2e-5 of the oracle
     xf = x.float()
     yf = P.anti_alias_activation_forward(xf.cuda(), None, None, a.cuda(), b.cuda(), precise=False)
