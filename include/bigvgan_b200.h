@@ -100,6 +100,18 @@ BVG_API int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, co
                      int64_t B, int64_t Cin, int64_t Cout, int64_t Tin, int K, int stride,
                      int dtype, void* stream);
 
+/* Same two layers on the bf16 tensor-core path (tcgen05.mma, TMEM accumulators, TMA-staged
+ * operands).  src/dst are plain [B,C,T] bf16 device tensors; the call converts to and from the
+ * library's internal channel-chunked layout (layer-level test entry points: they allocate
+ * temporaries with cudaMallocAsync; bvg_decode does not).  weight is fp32 in torch layout and is
+ * rounded to bf16; accumulation is fp32; the epilogue adds bias (+cond) (+res1 +res2), scales. */
+BVG_API int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
+                        const void* res1, const void* res2, float scale,
+                        int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);
+BVG_API int bvg_convtr1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
+                          const float* cond, int64_t Bc,
+                          int64_t B, int64_t Cin, int64_t Cout, int64_t Tin, int K, int stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-path plan.   replaces  indextts.BigVGAN.models.BigVGAN  (models.py:130-275) as built,
  * loaded and called by infer.py:61-67,204,498.

@@ -1,0 +1,455 @@
+// tcgen05 / TMEM implicit-GEMM Conv1d and ConvTranspose1d for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Replaces the cuDNN calls behind torch.nn.Conv1d / ConvTranspose1d in the generator
+// (models.py:25-42 AMPBlock1 convs, :149 conv_pre, :155-161 ups) on the bf16 throughput path.
+//
+// Layout ("c8t"): activations live in HBM as [B][C/8][Tp][8] bf16 -- 8 channels (16 bytes)
+// innermost, then time, then channel-chunk -- with PAD zero rows before t=0 and after t=T-1
+// (Tp = T + 2*PAD).  With that layout
+//   * a [rows x 64 ch] input tile is 8 contiguous runs of rows*16 B  -> 8 TMA bulk copies
+//     (cp.async.bulk, UBLKCP) land it in shared memory as [kchunk][row][8], which is exactly the
+//     canonical K-major no-swizzle UMMA operand layout (core matrix = 8 rows x 16 B contiguous,
+//     SBO = 128 B between 8-row groups, LBO = rows*16 B between K chunks);
+//   * a conv tap is a ROW OFFSET of the A operand: the same staged tile serves all K taps by
+//     moving the descriptor start address by tap*dilation*16 B -- no re-load, no im2col;
+//   * conv zero padding is the PAD rows; out-of-tile rows only ever feed discarded outputs.
+// GEMM view: D[t, co] (+)= X[t + shift_k, ci] * W_k[co, ci]   M = 128 time rows per accumulator,
+// N = NB <= 256 output channels, K = 16 input channels per tcgen05.mma.  Accumulators stay in
+// TMEM; a CTA owns MT*NPH of them (conv: 2 time sub-tiles sharing every weight load;
+// ConvTranspose: one accumulator per output phase).  Epilogue: tcgen05.ld -> +bias +cond
+// +residual(s), *scale -> bf16 -> 16-byte coalesced stores (lane = time row).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one per TMEM lane quarter).
+#include <string.h>
+
+#include <algorithm>
+
+#include "bvg_common.cuh"
+#include "umma.cuh"
+
+namespace bvg {
+namespace {
+
+constexpr int kXStages = 2;
+constexpr int kWStages = 4;
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  return d;          // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE (0)
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t x_stage_bytes = (uint32_t)P.XR * 128u;          // 8 kchunks x XR rows x 16 B
+  const uint32_t w_stage_bytes = (uint32_t)P.NB * 128u;          // 8 kchunks x NB rows x 16 B
+  uint8_t* xsm = smem;
+  uint8_t* wsm = smem + kXStages * x_stage_bytes;
+  uint8_t* tail = wsm + kWStages * w_stage_bytes;
+  uint64_t* full_x = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_x = full_x + kXStages;
+  uint64_t* full_w = empty_x + kXStages;
+  uint64_t* empty_w = full_w + kWStages;
+  uint64_t* tmem_full = empty_w + kWStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [NB]
+
+  const int tile = blockIdx.x % P.tiles_per_batch;
+  const int b = blockIdx.x / P.tiles_per_batch;
+  const int nb = blockIdx.y;
+  const int q0 = tile * P.MT * 128;                              // first coarse row of this CTA
+  const int nacc = P.MT * P.NPH;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(P.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < P.NB; i += 128) {
+      const int co = nb * P.NB + i;
+      bias_s[i] = (P.bias && co < P.Cout) ? P.bias[co] : 0.f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
+      const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;      // first staged row within a chunk
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
+      for (int cb = 0; cb < P.n_ci_blk; ++cb) {
+        const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
+        mbar_wait(&empty_x[xs], xph ^ 1);
+        mbar_expect_tx(&full_x[xs], (uint32_t)kcn * P.XR * 16u);
+        for (int kc = 0; kc < kcn; ++kc)
+          bulk_g2s(smem_u32(xsm + xs * x_stage_bytes) + kc * P.XR * 16,
+                   xb + ((int64_t)(cb * 8 + kc) * P.x_tp + row_start) * 8, (uint32_t)P.XR * 16u, &full_x[xs]);
+        if (++xs == kXStages) { xs = 0; xph ^= 1; }
+        const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
+        const __nv_bfloat16* wsrc = P.w + ((int64_t)nb * P.Cin_p + (int64_t)cb * 64) * P.NB * P.ntaps;
+        for (int tp = 0; tp < P.ntaps; ++tp) {
+          mbar_wait(&empty_w[ws], wph ^ 1);
+          mbar_expect_tx(&full_w[ws], wbytes);
+          bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
+          if (++ws == kWStages) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = NB, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
+      int xs = 0, ws = 0;
+      uint32_t xph = 0, wph = 0;
+      uint32_t touched = 0;
+      for (int cb = 0; cb < P.n_ci_blk; ++cb) {
+        const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
+        mbar_wait(&full_x[xs], xph);
+        const uint32_t xaddr = smem_u32(xsm + xs * x_stage_bytes);
+        for (int tp = 0; tp < P.ntaps; ++tp) {
+          mbar_wait(&full_w[ws], wph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t waddr = smem_u32(wsm + ws * w_stage_bytes);
+          const int shift = P.tap_shift[tp];
+          for (int ms = 0; ms < P.MT; ++ms) {
+            const int acc = ms * P.NPH + P.tap_acc[tp];
+            const uint32_t d = tmem_base + (uint32_t)(acc * P.NB);
+            for (int k2 = 0; k2 < kcn; k2 += 2) {
+              const uint64_t ad = make_desc(xaddr + (uint32_t)((ms * 128 + shift) * 16 + k2 * P.XR * 16), P.XR * 16, 128);
+              const uint64_t bd = make_desc(waddr + (uint32_t)(k2 * P.NB * 16), P.NB * 16, 128);
+              umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
+              touched |= 1u << acc;
+            }
+          }
+          umma_commit(&empty_w[ws]);            // weight slot reusable once these MMAs retire
+          if (++ws == kWStages) { ws = 0; wph ^= 1; }
+        }
+        umma_commit(&empty_x[xs]);
+        if (++xs == kXStages) { xs = 0; xph ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int wq = warp & 3;                                       // TMEM lane quarter of this warp
+    const int r = wq * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
+    const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
+    const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
+    const float* cond = P.cond ? P.cond + (int64_t)(P.cond_B == 1 ? 0 : b) * P.Cout : nullptr;
+    for (int a = 0; a < nacc; ++a) {
+      const int ms = a / P.NPH, s = a - ms * P.NPH;
+      const int64_t q = (int64_t)q0 + ms * 128 + r;
+      const int64_t t = q * P.u + s - P.p;
+      const bool valid = (t >= 0) && (t < P.Tout);
+      for (int c0 = 0; c0 < P.NB; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * P.NB + c0), v);
+        if (!valid) continue;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int co = nb * P.NB + c0 + 8 * g;
+          if (co >= P.Cout) continue;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[c0 + 8 * g + j];
+          if (cond) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (co + j < P.Cout) f[j] += cond[co + j];
+          }
+          const int64_t off = ((int64_t)(co >> 3) * P.y_tp + P.y_row0 + t) * 8;
+          if (r1) { float e[8]; unpack8(*reinterpret_cast<const uint4*>(r1 + off), e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
+          if (r2) { float e[8]; unpack8(*reinterpret_cast<const uint4*>(r2 + off), e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
+          uint4 o;
+          o.x = pack2(f[0] * P.scale, f[1] * P.scale); o.y = pack2(f[2] * P.scale, f[3] * P.scale);
+          o.z = pack2(f[4] * P.scale, f[5] * P.scale); o.w = pack2(f[6] * P.scale, f[7] * P.scale);
+          *reinterpret_cast<uint4*>(yb + off) = o;
+        }
+      }
+    }
+    if (P.zero_pads) {
+      // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
+      const int et = threadIdx.x - 64;
+      const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, ((P.Cout + 7) >> 3) - ch0);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      if (tile == 0)
+        for (int i = et; i < chn * P.y_row0; i += 128)
+          *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
+      if (tile == P.tiles_per_batch - 1)
+        for (int i = et; i < chn * P.y_row0; i += 128)
+          *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols));
+  }
+}
+
+// torch-layout fp32 weight -> packed bf16 tiles [n_blk][ci_blk][tap][kchunk][NB][8], zero padded.
+// conv: src [Cout][Cin][K]; transposed: src [Cin][Cout][K].
+__global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin,
+                                 int K, int transposed, int NB, int n_nblk, int Cin_p) {
+  const int64_t total = (int64_t)n_nblk * Cin_p * NB * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // decode i -> (nb, cb, tap, kc, row, e)
+    const int64_t per_nb = (int64_t)Cin_p * NB * K;
+    const int nb = (int)(i / per_nb);
+    int64_t rem = i - (int64_t)nb * per_nb;
+    const int cb = (int)(rem / ((int64_t)64 * NB * K));
+    rem -= (int64_t)cb * 64 * NB * K;
+    const int kcn = min(8, (Cin_p - cb * 64) >> 3);
+    const int per_tap = kcn * 8 * NB;
+    const int tap = (int)(rem / per_tap);
+    rem -= (int64_t)tap * per_tap;
+    const int kc = (int)(rem / (NB * 8));
+    rem -= (int64_t)kc * NB * 8;
+    const int row = (int)(rem >> 3), e = (int)(rem & 7);
+    const int co = nb * NB + row, ci = cb * 64 + kc * 8 + e;
+    float v = 0.f;
+    if (co < Cout && ci < Cin && tap < K)
+      v = transposed ? src[((int64_t)ci * Cout + co) * K + tap] : src[((int64_t)co * Cin + ci) * K + tap];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// plain [B,C,T] (fp32 or bf16) <-> c8t bf16
+template <typename TS>
+__global__ void to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const TS* __restrict__ src, int64_t sb, int64_t sc,
+                              int64_t st_, int C, int chunks, int T, int Tp, int pad) {
+  // one thread per (b, chunk, row) 16-byte vector, pads and padding channels zeroed
+  const int64_t n = (int64_t)gridDim.y * chunks * Tp;
+  (void)n;
+  const int b = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)chunks * Tp; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i / Tp), row = (int)(i % Tp);
+    const int t = row - pad;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      f[j] = (t >= 0 && t < T && c < C) ? to_f<TS>(src[b * sb + c * sc + t * st_]) : 0.f;
+    }
+    uint4 o;
+    o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + ((int64_t)b * chunks * Tp + i) * 8) = o;
+  }
+}
+template <typename TD>
+__global__ void from_c8t_kernel(TD* __restrict__ dst, const __nv_bfloat16* __restrict__ src, int C, int chunks, int T,
+                                int Tp, int pad) {
+  const int b = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)C * T; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / T), t = (int)(i % T);
+    dst[(int64_t)b * C * T + i] =
+        from_f<TD>(__bfloat162float(src[(((int64_t)b * chunks + (c >> 3)) * Tp + pad + t) * 8 + (c & 7)]));
+  }
+}
+
+}  // namespace
+
+size_t umma_smem_bytes(int XR, int NB) {
+  return (size_t)kXStages * XR * 128 + (size_t)kWStages * NB * 128 + (2 * kXStages + 2 * kWStages + 1) * 8 + 16 + (size_t)NB * 4 + 128;
+}
+
+void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
+  const int cap = nph >= 4 ? 128 : 256;                       // NPH * NB (x MT) must fit 512 TMEM columns
+  const int n = (Cout + cap - 1) / cap;
+  int nb = ((Cout + n - 1) / n + 15) / 16 * 16;
+  *NB = nb;
+  *n_nblk = (Cout + nb - 1) / nb;
+}
+
+int64_t umma_pack_elems(int Cout, int Cin, int K, int nph) {
+  int NB, nn;
+  umma_choose_nb(Cout, nph, &NB, &nn);
+  const int Cin_p = (Cin + 15) / 16 * 16;
+  return (int64_t)nn * Cin_p * NB * K;
+}
+
+int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
+                     int nph, cudaStream_t st) {
+  int NB, nn;
+  umma_choose_nb(Cout, nph, &NB, &nn);
+  const int Cin_p = (Cin + 15) / 16 * 16;
+  const int64_t total = (int64_t)nn * Cin_p * NB * K;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  pack_umma_kernel<<<blocks, 256, 0, st>>>(dst, src_torch_layout, Cout, Cin, K, transposed, NB, nn, Cin_p);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B,
+                     cudaStream_t st) {
+  BVG_CHECK_ARG(L.w && x.p && y.p, "conv_umma: null pointer");
+  BVG_CHECK_ARG(x.C == L.Cin && y.C == L.Cout, "conv_umma: channel mismatch (x.C=%d Cin=%d y.C=%d Cout=%d)", x.C, L.Cin, y.C, L.Cout);
+  UmmaConvParams P;
+  memset(&P, 0, sizeof P);
+  const int u = L.transposed ? L.stride : 1;
+  const int J = L.transposed ? L.K / u : 1;
+  P.NPH = L.transposed ? u : 1;
+  int n_nblk = 1;
+  umma_choose_nb(L.Cout, P.NPH, &P.NB, &n_nblk);
+  P.ntaps = L.K;
+  BVG_CHECK_ARG(L.K <= 16, "conv_umma: at most 16 taps");
+  P.MT = (P.NPH * P.NB * 2 <= 512 && !L.transposed) ? 2 : 1;
+  int halo;
+  if (!L.transposed) {
+    BVG_CHECK_ARG(y.T == x.T, "conv_umma: conv keeps the length");
+    const int pad = L.dil * (L.K - 1) / 2;
+    BVG_CHECK_ARG(pad <= x.pad, "conv_umma: conv padding %d exceeds the c8t halo %d", pad, x.pad);
+    for (int k = 0; k < L.K; ++k) { P.tap_shift[k] = (int16_t)(k * L.dil); P.tap_acc[k] = 0; }
+    P.lo = pad;
+    halo = L.dil * (L.K - 1);
+    P.u = 1; P.p = 0;
+    P.Tout = y.T;
+    P.tiles_per_batch = (y.T + P.MT * 128 - 1) / (P.MT * 128);
+  } else {
+    BVG_CHECK_ARG(L.K % u == 0 && (L.K - u) % 2 == 0 && J <= 2, "conv_umma: unsupported ConvTranspose1d K=%d stride=%d", L.K, u);
+    BVG_CHECK_ARG(y.T == x.T * u, "conv_umma: ConvTranspose1d output length");
+    for (int k = 0; k < L.K; ++k) { P.tap_shift[k] = (int16_t)((J - 1) - k / u); P.tap_acc[k] = (int16_t)(k % u); }
+    P.lo = J - 1;
+    halo = J - 1;
+    P.u = u; P.p = (L.K - u) / 2;
+    P.Tout = y.T;
+    const int qn = x.T + (P.p + u - 1) / u;                     // coarse rows that produce a valid output
+    P.tiles_per_batch = (qn + 127) / 128;
+    BVG_CHECK_ARG(x.pad >= 2, "conv_umma: c8t halo too small");
+  }
+  P.XR = P.MT * 128 + halo;
+  P.Cin_p = (L.Cin + 15) / 16 * 16;
+  BVG_CHECK_ARG(x.chunks * 8 >= P.Cin_p, "conv_umma: input tensor must carry channel padding to a multiple of 16");
+  P.n_ci_blk = (P.Cin_p + 63) / 64;
+  P.Cout = L.Cout;
+  P.x = x.p; P.x_bstride = (int64_t)x.chunks * x.Tp * 8; P.x_tp = x.Tp; P.x_row0 = x.pad;
+  P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad;
+  P.w = L.w;
+  P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
+  P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
+  int cols = P.MT * P.NPH * P.NB, pw = 32;
+  while (pw < cols) pw <<= 1;
+  BVG_CHECK_ARG(pw <= 512, "conv_umma: accumulators exceed TMEM");
+  P.tmem_cols = pw;
+  const size_t smem = umma_smem_bytes(P.XR, P.NB);
+  BVG_CHECK_ARG(smem <= 227 * 1024, "conv_umma: tile needs %zu B of shared memory", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  BVG_CHECK_ARG((int64_t)P.tiles_per_batch * B < (1ll << 31), "conv_umma: grid too large");
+  dim3 grid((unsigned)(P.tiles_per_batch * B), (unsigned)n_nblk);
+  ProfScope prof(st, L.transposed ? KC_CONVTR : KC_CONV);
+  conv_umma_kernel<<<grid, kThreads, smem, st>>>(P);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B,
+                  cudaStream_t st) {
+  if (B == 0) return BVG_OK;
+  dim3 grid((unsigned)std::min<int64_t>(((int64_t)dst.chunks * dst.Tp + 255) / 256, 4096), (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  if (src_dtype == BVG_F32)
+    to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+  else if (src_dtype == BVG_BF16)
+    to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+  else { set_error("to_c8t: unsupported dtype"); return BVG_ERR_INVALID; }
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st) {
+  if (B == 0) return BVG_OK;
+  dim3 grid((unsigned)std::min<int64_t>(((int64_t)src.C * src.T + 255) / 256, 4096), (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  if (dst_dtype == BVG_F32)
+    from_c8t_kernel<float><<<grid, 256, 0, st>>>((float*)dst, src.p, src.C, src.chunks, src.T, src.Tp, src.pad);
+  else if (dst_dtype == BVG_BF16)
+    from_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, src.p, src.C, src.chunks, src.T, src.Tp, src.pad);
+  else { set_error("from_c8t: unsupported dtype"); return BVG_ERR_INVALID; }
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace bvg

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "bvg_common.cuh"
+#include "umma.cuh"
 
 namespace bvg {
 
@@ -441,6 +442,53 @@ int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, const floa
   }
   cudaFreeAsync(wk, st);
   return rc;
+}
+
+static int umma_layer_test(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
+                           const void* res2, float scale, const float* cond, int64_t Bc, int64_t B, int64_t Cin,
+                           int64_t Cout, int64_t Tin, int K, int dil, int transposed, int stride, cudaStream_t st) {
+  BVG_CHECK_ARG(dst && src && weight && B >= 1 && Cin >= 1 && Cout >= 1 && Tin >= 1, "conv_umma: bad argument");
+  const int64_t Tout = transposed ? Tin * stride : Tin;
+  const int nph = transposed ? stride : 1;
+  const size_t xb = c8t_bytes(B, (int)Cin, Tin), yb = c8t_bytes(B, (int)Cout, Tout);
+  const size_t wb = (size_t)umma_pack_elems((int)Cout, (int)Cin, K, nph) * 2;
+  char* tmp = nullptr;
+  BVG_CUDA(cudaMallocAsync((void**)&tmp, xb + 3 * yb + wb + 1024, st));
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  C8T x = make_c8t(tmp, (int)Cin, (int)Tin);
+  C8T y = make_c8t(tmp + al(xb), (int)Cout, (int)Tout);
+  C8T r1 = make_c8t(tmp + al(xb) + al(yb), (int)Cout, (int)Tout);
+  C8T r2 = make_c8t(tmp + al(xb) + 2 * al(yb), (int)Cout, (int)Tout);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(tmp + al(xb) + 3 * al(yb));
+  int rc = to_c8t_launch(x, src, Cin * Tin, Tin, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK && res1) rc = to_c8t_launch(r1, res1, Cout * Tout, Tout, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK && res2) rc = to_c8t_launch(r2, res2, Cout * Tout, Tout, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK) rc = umma_pack_launch(wp, weight, (int)Cout, (int)Cin, K, transposed, nph, st);
+  if (rc == BVG_OK) {
+    UmmaLayer L;
+    L.w = wp; L.Cin = (int)Cin; L.Cout = (int)Cout; L.K = K; L.dil = dil; L.transposed = transposed; L.stride = stride;
+    UmmaEpilogue ep;
+    ep.bias = bias; ep.cond = cond; ep.cond_B = Bc; ep.scale = scale;
+    ep.res1 = res1 ? r1.p : nullptr; ep.res2 = res2 ? r2.p : nullptr;
+    rc = conv_umma_launch(L, x, y, ep, B, st);
+  }
+  if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
+int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
+                        const void* res2, float scale, int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K,
+                        int dilation, void* stream) {
+  return umma_layer_test(dst, src, weight, bias, res1, res2, scale, nullptr, 1, B, Cin, Cout, T, K, dilation, 0, 1,
+                         (cudaStream_t)stream);
+}
+
+int bvg_convtr1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias, const float* cond,
+                          int64_t Bc, int64_t B, int64_t Cin, int64_t Cout, int64_t Tin, int K, int stride,
+                          void* stream) {
+  return umma_layer_test(dst, src, weight, bias, nullptr, nullptr, 1.f, cond, Bc, B, Cin, Cout, Tin, K, 1, 1, stride,
+                         (cudaStream_t)stream);
 }
 
 int bvg_plan_create(bvg_plan** out, const bvg_config* cfg) {

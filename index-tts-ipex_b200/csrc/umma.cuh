@@ -1,0 +1,66 @@
+// Types shared by the tcgen05 conv path (conv_umma.cu), the c8t elementwise kernels and plan.cu.
+#pragma once
+#include "bvg_common.cuh"
+
+namespace bvg {
+
+constexpr int kC8tPad = 32;    // zero rows before t=0 and after t=T-1 (max conv padding is 25)
+
+// "c8t" activation tensor: [B][chunks][Tp][8] bf16, element (b,c,t) at
+// ((b*chunks + c/8)*Tp + pad + t)*8 + c%8.  chunks*8 >= C rounded up to a multiple of 16.
+struct C8T {
+  __nv_bfloat16* p = nullptr;
+  int C = 0, chunks = 0, T = 0, Tp = 0, pad = kC8tPad;
+  int64_t batch_stride() const { return (int64_t)chunks * Tp * 8; }
+};
+inline C8T make_c8t(void* p, int C, int T) {
+  C8T t;
+  t.p = static_cast<__nv_bfloat16*>(p);
+  t.C = C; t.chunks = ((C + 15) / 16) * 2; t.T = T; t.Tp = T + 2 * kC8tPad;
+  return t;
+}
+// bytes of a c8t buffer for B batch elements, including the tail slack tiles may over-read
+inline size_t c8t_bytes(int64_t B, int C, int64_t T) {
+  return (size_t)B * (((C + 15) / 16) * 2) * (T + 2 * kC8tPad) * 16 + 1024 * 16;
+}
+
+struct UmmaLayer {
+  const __nv_bfloat16* w = nullptr;   // packed [n_blk][ci_blk][tap][kchunk][NB][8]
+  const float* bias = nullptr;
+  int Cin = 0, Cout = 0, K = 1, dil = 1;
+  int transposed = 0, stride = 1;
+};
+
+struct UmmaEpilogue {
+  const float* bias = nullptr;
+  const float* cond = nullptr;        // [cond_B][Cout]
+  int64_t cond_B = 1;
+  const __nv_bfloat16* res1 = nullptr;  // same c8t geometry as the output
+  const __nv_bfloat16* res2 = nullptr;
+  float scale = 1.f;
+  int zero_pads = 0;                  // also (re)write the output's zero halo rows
+};
+
+struct UmmaConvParams {
+  const __nv_bfloat16* x; int64_t x_bstride; int x_tp; int x_row0;
+  __nv_bfloat16* y; int64_t y_bstride; int y_tp; int y_row0;
+  const __nv_bfloat16* w;
+  const __nv_bfloat16* res1; const __nv_bfloat16* res2;
+  const float* bias; const float* cond; int cond_B;
+  float scale;
+  int Tout, u, p;                     // output row of coarse row q, phase s: t = u*q + s - p
+  int ntaps; int16_t tap_shift[16]; int16_t tap_acc[16];
+  int lo, XR;                         // staged rows: [q0 - lo, q0 - lo + XR)
+  int n_ci_blk, Cin_p, NB, Cout, NPH, MT, tiles_per_batch, zero_pads, tmem_cols;
+};
+
+size_t umma_smem_bytes(int XR, int NB);
+void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
+int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
+int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
+                     int nph, cudaStream_t st);
+int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
+int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
+int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
+
+}  // namespace bvg

@@ -1,0 +1,68 @@
+"""tcgen05 implicit-GEMM conv layers (bf16 operands, fp32 accumulate) against a float64 conv of the
+same bf16-rounded operands.  With exactly representable operands the only differences are the
+fp32 accumulation order and the final bf16 rounding of the output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import index_tts_ipex_b200 as pkg
+    return pkg
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _check(y, ref):
+    err = (y.double().cpu() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 1e-3          # half-ulp bf16 rounding + accumulation-order slack
+    assert float((err - bound).max()) <= 0, (float(err.max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("Cin,Cout,T,K,dil", [
+    (64, 64, 256, 1, 1), (64, 64, 256, 3, 1), (96, 96, 300, 3, 1), (96, 96, 1000, 11, 5), (24, 24, 700, 7, 3),
+    (48, 48, 513, 3, 5), (192, 192, 130, 7, 1), (384, 384, 64, 3, 3), (768, 768, 40, 3, 1), (1280, 1536, 20, 7, 1),
+    (128, 16, 257, 3, 1)])
+def test_conv1d_umma_vs_float64(P, Cin, Cout, T, K, dil):
+    gen = torch.Generator().manual_seed(Cin + 7 * T + K)
+    B = 2
+    x = _bf(torch.randn(B, Cin, T, generator=gen))
+    w = _bf(torch.randn(Cout, Cin, K, generator=gen) / (Cin * K) ** 0.5).float()
+    b = torch.randn(Cout, generator=gen)
+    r1 = _bf(torch.randn(B, Cout, T, generator=gen))
+    r2 = _bf(torch.randn(B, Cout, T, generator=gen))
+    ref = (F.conv1d(x.double(), w.double(), b.double(), dilation=dil, padding=dil * (K - 1) // 2)
+           + r1.double() + r2.double()) / 3
+    L = P.capi.lib()
+    xd, wd, bd, r1d, r2d = x.cuda(), w.cuda(), b.cuda(), r1.cuda(), r2.cuda()
+    y = torch.empty(B, Cout, T, device="cuda", dtype=torch.bfloat16)
+    P.capi.check(L.bvg_conv1d_umma_fwd(y.data_ptr(), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), r1d.data_ptr(),
+                                       r2d.data_ptr(), 1.0 / 3, B, Cin, Cout, T, K, dil,
+                                       torch.cuda.current_stream().cuda_stream), "bvg_conv1d_umma_fwd")
+    torch.cuda.synchronize()
+    _check(y, ref)
+
+
+@pytest.mark.parametrize("Cin,Cout,Tin,K,u", [(1536, 768, 20, 8, 4), (768, 384, 70, 8, 4), (384, 192, 129, 4, 4),
+                                               (192, 96, 300, 4, 4), (96, 48, 515, 4, 2), (48, 24, 1000, 4, 2)])
+def test_convtr1d_umma_vs_float64(P, Cin, Cout, Tin, K, u):
+    gen = torch.Generator().manual_seed(Cin + Tin)
+    B = 2
+    x = _bf(torch.randn(B, Cin, Tin, generator=gen))
+    w = _bf(torch.randn(Cin, Cout, K, generator=gen) / (Cin * K / u) ** 0.5).float()
+    b = torch.randn(Cout, generator=gen)
+    cond = torch.randn(B, Cout, generator=gen)
+    ref = F.conv_transpose1d(x.double(), w.double(), b.double(), stride=u, padding=(K - u) // 2) + cond.double().unsqueeze(-1)
+    L = P.capi.lib()
+    xd, wd, bd, cd = x.cuda(), w.cuda(), b.cuda(), cond.cuda()
+    y = torch.empty(B, Cout, Tin * u, device="cuda", dtype=torch.bfloat16)
+    P.capi.check(L.bvg_convtr1d_umma_fwd(y.data_ptr(), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), cd.data_ptr(), B,
+                                         B, Cin, Cout, Tin, K, u, torch.cuda.current_stream().cuda_stream),
+                 "bvg_convtr1d_umma_fwd")
+    torch.cuda.synchronize()
+    _check(y, ref)
