@@ -105,6 +105,10 @@ BVG_API int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, co
  * library's internal channel-chunked layout (layer-level test entry points: they allocate
  * temporaries with cudaMallocAsync; bvg_decode does not).  weight is fp32 in torch layout and is
  * rounded to bf16; accumulation is fp32; the epilogue adds bias (+cond) (+res1 +res2), scales. */
+/* Activation1d through the channel-chunked kernel of the bf16 path (plain [B,C,T] bf16 in/out;
+ * converts internally; test entry point). */
+BVG_API int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                      int64_t B, int64_t C, int64_t T, void* stream);
 BVG_API int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
                         const void* res1, const void* res2, float scale,
                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);

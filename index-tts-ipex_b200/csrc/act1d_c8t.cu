@@ -1,0 +1,209 @@
+// Activation1d and the conv_post tail in the channel-chunked "c8t" layout of the bf16 path
+// ([B][C/8][Tp][8] bf16, see conv_umma.cu).  Same arithmetic as act1d.cu (alias_free_torch/act.py:24-29
+// of the reference, PyTorch edge semantics); only the data movement differs:
+//   * a CTA owns NCH channel-chunks x TR rows; per chunk the rows are one contiguous run, staged by
+//     one TMA bulk copy (cp.async.bulk, mbarrier completion) including the 8-row FIR halo;
+//   * a thread owns one chunk (8 channels, one 16-byte vector per row) x 8 consecutive rows: 24
+//     LDS.128 give it the whole window; channels are unpacked and run through the shared stencil one
+//     at a time; results are re-packed to 16-byte rows in shared memory and leave through one TMA
+//     bulk store per chunk (cp.async.bulk.global.shared::cta).
+//   * the kernel also (re)writes the zero halo rows and zero padding channels that the tcgen05 conv
+//     reads as its zero padding.
+#include "act1d_core.cuh"
+#include "bvg_common.cuh"
+#include "umma.cuh"
+
+namespace bvg {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                 const float* __restrict__ alpha_log, const float* __restrict__ beta_log, int C, int chunks, int T,
+                 int Tp, int pad) {
+  constexpr int TR = 2048 / NCH;          // rows per CTA
+  constexpr int RIN = TR + 16 + 1;        // staged rows per chunk (+1: odd pitch)
+  constexpr int ROUT = TR + 1;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4* in = reinterpret_cast<uint4*>(smem_raw);                 // [NCH][RIN]
+  uint4* out = in + NCH * RIN;                                    // [NCH][ROUT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(out + NCH * ROUT);
+
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * TR;                                 // first (padded-space) row of the tile
+  const int ch0 = blockIdx.y * NCH;
+  const int b = blockIdx.z;
+  const int nch = min(NCH, chunks - ch0);
+  const int64_t base = (int64_t)b * chunks * Tp;
+
+  const int lo = max(r0 - 8, 0), hi = min(r0 + TR + 8, Tp);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)(hi - lo) * 16u;
+    mbar_expect_tx(bar, bytes * nch);
+    for (int c = 0; c < nch; ++c)
+      bulk_g2s(in + c * RIN + (lo - (r0 - 8)), x + (base + (int64_t)(ch0 + c) * Tp + lo) * 8, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+
+  const int cg = tid % NCH, tg = tid / NCH;
+  if (cg < nch) {
+    const int64_t t0 = (int64_t)r0 + 8 * tg - pad;                // time index of this thread's first output
+    uint4 win[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) win[j] = in[cg * RIN + 8 * tg + j];
+    uint32_t yp[8][4];
+    float ye[8];
+    const bool any_valid = (t0 + 7 >= 0) && (t0 < T);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = (ch0 + cg) * 8 + c;
+      float yv[8];
+      if (any_valid && ch < C) {
+        float xw[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const uint32_t w = (c >> 1) == 0 ? win[j].x : (c >> 1) == 1 ? win[j].y : (c >> 1) == 2 ? win[j].z : win[j].w;
+          xw[j] = (c & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+        }
+        const float ea = __expf(alpha_log[ch]);
+        const float ib = __fdividef(1.0f, __expf(beta_log[ch]) + 1e-9f);
+        act1d_window<false>(xw, yv, ea, ib, t0, (int64_t)T);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (t0 + q < 0 || t0 + q >= T) yv[q] = 0.f;             // zero halo rows
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) yv[q] = 0.f;                  // zero halo rows / padding channels
+      }
+      if ((c & 1) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ye[q] = yv[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) yp[q][c >> 1] = pack2(ye[q], yv[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[cg * ROUT + 8 * tg + q] = make_uint4(yp[q][0], yp[q][1], yp[q][2], yp[q][3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async-proxy reads
+  __syncthreads();
+  if (tid < nch) {
+    const int nrows = min(TR, Tp - r0);
+    bulk_s2g(y + (base + (int64_t)(ch0 + tid) * Tp + r0) * 8, out + tid * ROUT, (uint32_t)nrows * 16u);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+// activation_post output (c8t) -> conv_post (Cin -> 1, K taps, zero pad) -> tanh -> fp32 wav / int16 pcm
+// (models.py:246-248; infer.py:206-212,234 for the pcm epilogue)
+__global__ void __launch_bounds__(256)
+conv_post_c8t_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ w, const float* __restrict__ bias, int Cin, int chunks, int T, int Tp,
+                     int pad, int K, int64_t s_lo, int64_t s_hi) {
+  extern __shared__ float wsm[];   // [Cin*K] as [ci][k]
+  for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t Tout = T - s_lo - s_hi;
+  const int64_t to = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (to >= Tout) return;
+  const int64_t t = to + s_lo;
+  const int hp = (K - 1) / 2;
+  float acc = bias ? bias[0] : 0.f;
+  const int nchunk = (Cin + 7) >> 3;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const __nv_bfloat16* xr = x + (((int64_t)b * chunks + ch) * Tp + pad + t - hp) * 8;   // halo rows are zero
+    for (int k = 0; k < K; ++k) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + (int64_t)k * 8);
+      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = ch * 8 + 2 * j;
+        if (c < Cin) acc = fmaf(wsm[c * K + k], __uint_as_float(wd[j] << 16), acc);
+        if (c + 1 < Cin) acc = fmaf(wsm[(c + 1) * K + k], __uint_as_float(wd[j] & 0xffff0000u), acc);
+      }
+    }
+  }
+  const float yv = tanhf(acc);
+  if (wav) wav[(int64_t)b * Tout + to] = yv;
+  if (pcm) pcm[(int64_t)b * Tout + to] = (int16_t)fminf(fmaxf(32767.f * yv, -32767.f), 32767.f);
+}
+
+template <int NCH>
+int launch_act(const C8T& y, const C8T& x, const float* a, const float* b_, int64_t B, cudaStream_t st) {
+  constexpr int TR = 2048 / NCH;
+  const size_t smem = (size_t)NCH * (TR + 17) * 16 + (size_t)NCH * (TR + 1) * 16 + 16;
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(act1d_c8t_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((unsigned)((x.Tp + TR - 1) / TR), (unsigned)((x.chunks + NCH - 1) / NCH), (unsigned)B);
+  ProfScope prof(st, KC_ACT1D);
+  act1d_c8t_kernel<NCH><<<grid, 256, smem, st>>>(y.p, x.p, a, b_, x.C, x.chunks, x.T, x.Tp, x.pad);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace
+
+int act1d_c8t_launch(const C8T& y, const C8T& x, const float* alpha_log, const float* beta_log, int64_t B,
+                     cudaStream_t st) {
+  BVG_CHECK_ARG(y.p && x.p && y.p != x.p, "act1d_c8t: bad buffers");
+  BVG_CHECK_ARG(y.C == x.C && y.T == x.T && y.chunks == x.chunks && y.pad == x.pad, "act1d_c8t: geometry mismatch");
+  BVG_CHECK_ARG(B >= 1 && B <= 65535, "act1d_c8t: bad batch");
+  if (x.chunks % 8 == 0 || x.chunks > 16) return launch_act<8>(y, x, alpha_log, beta_log, B, st);
+  if (x.chunks % 4 == 0) return launch_act<4>(y, x, alpha_log, beta_log, B, st);
+  return launch_act<2>(y, x, alpha_log, beta_log, B, st);
+}
+
+int conv_post_c8t_launch(float* wav, int16_t* pcm, const C8T& x, const float* w, const float* bias, int K,
+                         int64_t s_lo, int64_t s_hi, int64_t B, cudaStream_t st) {
+  BVG_CHECK_ARG(wav || pcm, "conv_post: no output buffer");
+  BVG_CHECK_ARG((K - 1) / 2 <= x.pad && x.C * K * 4 <= 48 * 1024, "conv_post: unsupported shape");
+  const int64_t Tout = x.T - s_lo - s_hi;
+  BVG_CHECK_ARG(Tout >= 0 && s_lo >= 0 && s_hi >= 0, "conv_post: bad crop");
+  if (Tout == 0) return BVG_OK;
+  dim3 grid((unsigned)((Tout + 255) / 256), (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  conv_post_c8t_kernel<<<grid, 256, (size_t)x.C * K * 4, st>>>(wav, pcm, x.p, w, bias, x.C, x.chunks, x.T, x.Tp, x.pad, K,
+                                                              s_lo, s_hi);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+}  // namespace bvg

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int co = nb * P.NB + c0 + 8 * g;
-          if (co >= P.Cout) continue;
+          if (co >= P.y_chunks * 8) continue;      // padding channels inside the tensor are written as zeros
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[c0 + 8 * g + j];
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     if (P.zero_pads) {
       // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
       const int et = threadIdx.x - 64;
-      const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, ((P.Cout + 7) >> 3) - ch0);
+      const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, P.y_chunks - ch0);
       const uint4 z = make_uint4(0, 0, 0, 0);
       if (tile == 0)
         for (int i = et; i < chn * P.y_row0; i += 128)
@@ -402,7 +402,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.n_ci_blk = (P.Cin_p + 63) / 64;
   P.Cout = L.Cout;
   P.x = x.p; P.x_bstride = (int64_t)x.chunks * x.Tp * 8; P.x_tp = x.Tp; P.x_row0 = x.pad;
-  P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad;
+  P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad; P.y_chunks = y.chunks;
   P.w = L.w;
   P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;

@@ -56,6 +56,7 @@ struct ConvLayer {
   float* w = nullptr;     // [K][Cin][Cout] fp32
   float* bias = nullptr;  // [Cout] or null
   int Cin = 0, Cout = 0, K = 1;
+  __nv_bfloat16* wu = nullptr;   // tcgen05 pack (conv_umma.cu), generator convs only
 };
 struct Tdnn {             // conv -> ReLU -> eval-BN (ECAPA_TDNN.py:126-128)
   ConvLayer conv;
@@ -83,6 +84,7 @@ struct bvg_plan {
   bvg_config cfg{};
   std::map<std::string, std::vector<float>> host;
   bool finalized = false;
+  bool umma = false;        // bf16 tcgen05 packs built
   std::vector<void*> allocs;
   int n_stage = 0;
   int C[9] = {};          // C[0] = upsample_initial_channel, C[i+1] = channels after ups[i]
@@ -142,7 +144,7 @@ int upload_key(bvg_plan* P, const std::string& key, int64_t numel, float** out) 
 
 // weight key holds torch layout [Cout,Cin,K] (or [Cin,Cout,K] when transposed); optional input-channel slice
 int make_conv(bvg_plan* P, const std::string& wkey, const std::string& bkey, int Cout, int Cin_total, int K,
-              bool transposed, ConvLayer* L, int ci_lo = 0, int ci_hi = -1) {
+              bool transposed, ConvLayer* L, int ci_lo = 0, int ci_hi = -1, int umma_nph = 0) {
   if (ci_hi < 0) ci_hi = Cin_total;
   const int Cin = ci_hi - ci_lo;
   const std::vector<float>* w;
@@ -163,6 +165,12 @@ int make_conv(bvg_plan* P, const std::string& wkey, const std::string& bkey, int
   void* d = nullptr;
   int rc = dev_alloc(P, &d, n * sizeof(float));
   if (rc == BVG_OK) rc = repack_conv_weight_launch((float*)d, raw, Cout, Cin, K, transposed ? 1 : 0, 0);
+  void* du = nullptr;
+  if (rc == BVG_OK && umma_nph > 0) {
+    rc = dev_alloc(P, &du, (size_t)umma_pack_elems(Cout, Cin, K, umma_nph) * 2);
+    if (rc == BVG_OK) rc = umma_pack_launch((__nv_bfloat16*)du, raw, Cout, Cin, K, transposed ? 1 : 0, umma_nph, 0);
+  }
+  L->wu = (__nv_bfloat16*)du;
   cudaError_t e = cudaStreamSynchronize(0);
   cudaFree(raw);
   if (rc != BVG_OK) return rc;
@@ -332,12 +340,14 @@ struct GenWs {
 void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
   const size_t es = dtype_size(dtype);
   int64_t maxel = (int64_t)P->C[0] * T0;
+  size_t c8 = std::max(c8t_bytes(B, P->C[0], T0), c8t_bytes(B, P->cfg.gpt_dim, T0));
   int64_t T = T0;
   for (int i = 0; i < P->n_stage; ++i) {
     T *= P->cfg.upsample_rates[i];
     maxel = std::max<int64_t>(maxel, (int64_t)P->C[i + 1] * T);
+    c8 = std::max(c8, c8t_bytes(B, P->C[i + 1], T));
   }
-  const size_t bytes = (size_t)B * maxel * es;
+  const size_t bytes = (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * es;
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
   for (int i = 0; i <= P->n_stage; ++i) g->cond[i] = b.takef(Bm * P->C[i]);
   g->spk = b.takef(Bm * P->cfg.speaker_embedding_dim);
@@ -359,6 +369,74 @@ int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, in
   ep.bias = L.bias;
   return conv1d_simt_launch(dst, (int64_t)L.Cout * T, src, nullptr, (int64_t)L.Cin * T, T, 1, L.w, ep, B, L.Cin,
                             L.Cout, T, L.K, dil, 0, dtype, dtype, st);
+}
+
+UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1) {
+  UmmaLayer u;
+  u.w = L.wu; u.bias = L.bias; u.Cin = L.Cin; u.Cout = L.Cout; u.K = L.K; u.dil = dil;
+  u.transposed = transposed; u.stride = stride;
+  return u;
+}
+
+// The bf16 throughput path: c8t activations, tcgen05 convs (models.py:220-248).
+int decode_bf16_umma(const bvg_plan* P, const float* latent, const GenWs& g, int64_t B, int64_t T0, int64_t Bm,
+                     float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st) {
+  const bvg_config& c = P->cfg;
+  // latent [B,T0,gpt_dim] fp32 (channels-last) -> c8t bf16
+  C8T lat = make_c8t(g.T1, c.gpt_dim, (int)T0);
+  BVG_TRY(to_c8t_launch(lat, latent, T0 * c.gpt_dim, 1, c.gpt_dim, BVG_F32, B, st));
+  int64_t T = T0;
+  C8T xs = make_c8t(g.XS, P->C[0], (int)T);
+  {
+    UmmaEpilogue ep;
+    ep.bias = P->conv_pre.bias; ep.cond = g.cond[0]; ep.cond_B = Bm; ep.zero_pads = 1;
+    BVG_TRY(conv_umma_launch(ulayer(P->conv_pre, 1), lat, xs, ep, B, st));
+  }
+  const float inv_nk = 1.0f / (float)c.num_kernels;
+  for (int i = 0; i < P->n_stage; ++i) {
+    const int u = c.upsample_rates[i];
+    const int ch = P->C[i + 1];
+    const int64_t Tn = T * u;
+    C8T a = make_c8t(g.A, ch, (int)Tn);
+    {
+      UmmaEpilogue ep;
+      ep.bias = P->ups[i].bias;
+      if (c.cond_in_each_up_layer) { ep.cond = g.cond[i + 1]; ep.cond_B = Bm; }
+      BVG_TRY(conv_umma_launch(ulayer(P->ups[i], 1, 1, u), xs, a, ep, B, st));
+    }
+    T = Tn;
+    C8T y = make_c8t(g.Y, ch, (int)T), t1 = make_c8t(g.T1, ch, (int)T), t2 = make_c8t(g.T2, ch, (int)T);
+    xs = make_c8t(g.XS, ch, (int)T);
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
+      const C8T* cur = &a;
+      for (int m = 0; m < 3; ++m) {
+        BVG_TRY(act1d_c8t_launch(t1, *cur, R.alpha[2 * m], R.beta[2 * m], B, st));
+        UmmaEpilogue e1;
+        e1.bias = R.c1[m].bias;
+        BVG_TRY(conv_umma_launch(ulayer(R.c1[m], R.dil[m]), t1, t2, e1, B, st));
+        BVG_TRY(act1d_c8t_launch(t1, t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, st));
+        UmmaEpilogue e2;
+        e2.bias = R.c2[m].bias;
+        e2.res1 = cur->p;
+        if (m < 2) {
+          BVG_TRY(conv_umma_launch(ulayer(R.c2[m], 1), t1, y, e2, B, st));
+          cur = &y;
+        } else {
+          if (j > 0) e2.res2 = xs.p;
+          if (j == c.num_kernels - 1) e2.scale = inv_nk;
+          e2.zero_pads = 1;
+          BVG_TRY(conv_umma_launch(ulayer(R.c2[m], 1), t1, xs, e2, B, st));
+        }
+      }
+    }
+  }
+  const int chp = P->C[P->n_stage];
+  C8T t1 = make_c8t(g.T1, chp, (int)T);
+  BVG_TRY(act1d_c8t_launch(t1, xs, P->post_alpha, P->post_beta, B, st));
+  BVG_TRY(conv_post_c8t_launch(wav, pcm16, t1, P->post_w, P->post_bias, 7, t_lo_pad * P->total_up,
+                               t_hi_pad * P->total_up, B, st));
+  return BVG_OK;
 }
 
 }  // namespace
@@ -477,6 +555,25 @@ static int umma_layer_test(void* dst, const void* src, const float* weight, cons
   return rc;
 }
 
+int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log, int64_t B,
+                      int64_t Cn, int64_t T, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(dst && src && alpha_log && beta_log && B >= 1 && Cn >= 1 && T >= 1, "act1d_c8t: bad argument");
+  const size_t nb = c8t_bytes(B, (int)Cn, T);
+  char* tmp = nullptr;
+  BVG_CUDA(cudaMallocAsync((void**)&tmp, 2 * nb + 512, st));
+  C8T x = make_c8t(tmp, (int)Cn, (int)T), y = make_c8t(tmp + ((nb + 255) & ~size_t(255)), (int)Cn, (int)T);
+  // poison the halo rows of x: the kernel must not depend on them (conv outputs leave them undefined)
+  int rc = BVG_OK;
+  if (cudaMemsetAsync(tmp, 0x7f, 2 * nb + 512, st) != cudaSuccess) rc = BVG_ERR_CUDA;
+  if (rc == BVG_OK) rc = to_c8t_launch(x, src, Cn * T, T, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK && cudaMemsetAsync(x.p, 0x7f, (size_t)x.pad * 16, st) != cudaSuccess) rc = BVG_ERR_CUDA;
+  if (rc == BVG_OK) rc = act1d_c8t_launch(y, x, alpha_log, beta_log, B, st);
+  if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
 int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
                         const void* res2, float scale, int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K,
                         int dilation, void* stream) {
@@ -535,17 +632,19 @@ int bvg_plan_set_tensor(bvg_plan* P, const char* key, const float* data, int64_t
 int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
   BVG_CHECK_ARG(P, "plan_finalize: null plan");
   if (P->finalized) return BVG_OK;
-  (void)enable_bf16_umma;
+  const int um = enable_bf16_umma ? 1 : 0;
+  P->umma = um != 0;
   BVG_CUDA(cudaSetDevice(P->cfg.device));
   const bvg_config& c = P->cfg;
   const int E = c.speaker_embedding_dim;
-  BVG_TRY(make_conv(P, "conv_pre.weight", "conv_pre.bias", P->C[0], c.gpt_dim, 7, false, &P->conv_pre));
+  BVG_TRY(make_conv(P, "conv_pre.weight", "conv_pre.bias", P->C[0], c.gpt_dim, 7, false, &P->conv_pre, 0, -1, um));
   BVG_TRY(make_conv(P, "cond_layer.weight", "cond_layer.bias", P->C[0], E, 1, false, &P->cond_layer));
   P->ups.resize(P->n_stage);
   P->conds.resize(P->n_stage);
   for (int i = 0; i < P->n_stage; ++i) {
     const std::string u = "ups." + std::to_string(i) + ".0";
-    BVG_TRY(make_conv(P, u + ".weight", u + ".bias", P->C[i + 1], P->C[i], c.upsample_kernel_sizes[i], true, &P->ups[i]));
+    BVG_TRY(make_conv(P, u + ".weight", u + ".bias", P->C[i + 1], P->C[i], c.upsample_kernel_sizes[i], true, &P->ups[i],
+                      0, -1, um * c.upsample_rates[i]));
     if (c.cond_in_each_up_layer) {
       const std::string k = "conds." + std::to_string(i);
       BVG_TRY(make_conv(P, k + ".weight", k + ".bias", P->C[i + 1], E, 1, false, &P->conds[i]));
@@ -562,8 +661,8 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
       for (int m = 0; m < 3; ++m) {
         R.dil[m] = c.resblock_dilation_sizes[j][m];
         const std::string a = p + ".convs1." + std::to_string(m), b = p + ".convs2." + std::to_string(m);
-        BVG_TRY(make_conv(P, a + ".weight", a + ".bias", ch, ch, R.K, false, &R.c1[m]));
-        BVG_TRY(make_conv(P, b + ".weight", b + ".bias", ch, ch, R.K, false, &R.c2[m]));
+        BVG_TRY(make_conv(P, a + ".weight", a + ".bias", ch, ch, R.K, false, &R.c1[m], 0, -1, um));
+        BVG_TRY(make_conv(P, b + ".weight", b + ".bias", ch, ch, R.K, false, &R.c2[m], 0, -1, um));
       }
       for (int m = 0; m < 6; ++m)
         BVG_TRY(make_act(P, p + ".activations." + std::to_string(m), ch, &R.alpha[m], &R.beta[m]));
@@ -656,6 +755,8 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
       for (int i = 0; i < P->n_stage; ++i)
         BVG_TRY(conv_f32(g.cond[i + 1], P->C[i + 1], spk, nullptr, E, 1, 1, P->conds[i], ep, Bm, 1, 1, 0, st));
   }
+  if (dtype == BVG_BF16 && P->umma)
+    return decode_bf16_umma(P, latent, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st);
   // conv_pre on latent^T (models.py:220-226): read [B,T0,gpt_dim] through strides
   {
     ConvEpilogue ep;

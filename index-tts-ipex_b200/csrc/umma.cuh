@@ -43,7 +43,7 @@ struct UmmaEpilogue {
 
 struct UmmaConvParams {
   const __nv_bfloat16* x; int64_t x_bstride; int x_tp; int x_row0;
-  __nv_bfloat16* y; int64_t y_bstride; int y_tp; int y_row0;
+  __nv_bfloat16* y; int64_t y_bstride; int y_tp; int y_row0; int y_chunks;
   const __nv_bfloat16* w;
   const __nv_bfloat16* res1; const __nv_bfloat16* res2;
   const float* bias; const float* cond; int cond_B;
@@ -62,5 +62,11 @@ int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
+// Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)
+int act1d_c8t_launch(const C8T& y, const C8T& x, const float* alpha_log, const float* beta_log, int64_t B,
+                     cudaStream_t st);
+// conv_post (Cin->1) + tanh on a c8t tensor whose halo rows are zero; w is [Cin][K] fp32
+int conv_post_c8t_launch(float* wav, int16_t* pcm, const C8T& x, const float* w, const float* bias, int K,
+                         int64_t s_lo, int64_t s_hi, int64_t B, cudaStream_t st);
 
 }  // namespace bvg
