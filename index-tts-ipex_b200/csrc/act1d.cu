@@ -178,17 +178,11 @@ act1d_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __rest
   if (r >= nrows || tg >= Tlen) return;
   const int64_t row = row0 + r;
   const int ch = (int)(row % C);
-  float ea, ib;
-  if (PRECISE) {
-    ea = expf(alpha_log[ch]);
-    ib = 1.0f / (expf(beta_log[ch]) + 1e-9f);
-  } else {
-    ea = __expf(alpha_log[ch]);
-    ib = __fdividef(1.0f, __expf(beta_log[ch]) + 1e-9f);
-  }
+  float sc0, sc1;
+  snake_params<PRECISE>(alpha_log[ch], beta_log[ch], sc0, sc1);
   float xw[24], y[8];
   load_window<T>(&tile[r][c0], xw);
-  act1d_window<PRECISE>(xw, y, ea, ib, tg, Tlen);
+  act1d_window<8, PRECISE>(xw, y, sc0, sc1, tg, Tlen);
   T* out = dst + row * Tlen + tg;
   if (ALIGNED) {
     store8_vec<T>(out, y);       // T % (16/sizeof(T)) == 0 and tg % 8 == 0 -> all 8 in range

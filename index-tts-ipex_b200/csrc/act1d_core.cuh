@@ -5,38 +5,47 @@
 
 namespace bvg {
 
+// SnakeBeta on one upsampled sample (activations.py:109-122):  u + 1/(e^beta + 1e-9) * sin(e^alpha u)^2
+//   PRECISE: libdevice sinf (fp32 parity path).  sc0 = e^alpha, sc1 = 1/(e^beta+1e-9)
+//   fast:    sin^2 z = (1 - cos 2z)/2  ->  u + hb - hb*cos(2 e^alpha u), one FMUL + MUFU.COS + FADD + FFMA.
+//            sc0 = 2 e^alpha, sc1 = hb = 0.5/(e^beta+1e-9)
 template <bool PRECISE>
-__device__ __forceinline__ float snake(float u, float ea, float ib) {
+__device__ __forceinline__ float snake(float u, float sc0, float sc1) {
   if (PRECISE) {
-    float s = sinf(u * ea);
-    return fmaf(ib * s, s, u);
+    float s = sinf(u * sc0);
+    return fmaf(sc1 * s, s, u);
   } else {
-    // sin^2 has period pi: reduce z = u*ea to r in [-pi/2, pi/2] with a 2-term Cody-Waite
-    // split of pi, then MUFU.SIN (accurate to ~1e-7 abs on that interval).
-    float z = u * ea;
-    float k = rintf(z * 0.318309886183790672f);
-    float r = fmaf(k, -3.140625f, z);
-    r = fmaf(k, -9.67653589793e-4f, r);
-    float s = __sinf(r);
-    return fmaf(ib * s, s, u);
+    return fmaf(-sc1, __cosf(u * sc0), u + sc1);
+  }
+}
+template <bool PRECISE>
+__device__ __forceinline__ void snake_params(float alpha_log, float beta_log, float& sc0, float& sc1) {
+  if (PRECISE) {
+    sc0 = expf(alpha_log);
+    sc1 = 1.0f / (expf(beta_log) + 1e-9f);
+  } else {
+    sc0 = 2.0f * __expf(alpha_log);
+    sc1 = __fdividef(0.5f, __expf(beta_log) + 1e-9f);
   }
 }
 
-// The per-thread stencil: 24-sample input window (xw[i] = x[tg-8+i]) -> 8 outputs y[tg..tg+7].
-template <bool PRECISE>
-__device__ __forceinline__ void act1d_window(float (&xw)[24], float (&y)[8], float ea, float ib,
+// The per-thread stencil: (V+16)-sample input window (xw[i] = x[tg-8+i]) -> V outputs y[tg..tg+V-1].
+template <int V, bool PRECISE>
+__device__ __forceinline__ void act1d_window(float (&xw)[V + 16], float (&y)[V], float sc0, float sc1,
                                              int64_t tg, int64_t T) {
+  constexpr int W = V + 16;
+  constexpr int NA = 2 * V + 10;
   // replicate padding of the input (F.pad(x,(5,5),'replicate'), resample.py:28)
-  if (tg - 5 < 0 || tg + 12 > T - 1) {
+  if (tg - 5 < 0 || tg + V + 4 > T - 1) {
     float xl = 0.f, xr = 0.f;
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
+    for (int i = 0; i < W; ++i) {
       int64_t t = tg - 8 + i;
       if (t == 0) xl = xw[i];
       if (t == T - 1) xr = xw[i];
     }
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
+    for (int i = 0; i < W; ++i) {
       int64_t t = tg - 8 + i;
       if (t < 0) xw[i] = xl;
       if (t > T - 1) xw[i] = xr;
@@ -44,10 +53,10 @@ __device__ __forceinline__ void act1d_window(float (&xw)[24], float (&y)[8], flo
   }
   const float g0 = 2.f * BVG_F0, g1 = 2.f * BVG_F1, g2 = 2.f * BVG_F2, g3 = 2.f * BVG_F3,
               g4 = 2.f * BVG_F4, g5 = 2.f * BVG_F5;
-  // a[i] <-> upsampled index m = 2*tg - 5 + i, i = 0..25
-  float a[26];
+  // a[i] <-> upsampled index m = 2*tg - 5 + i, i = 0..2V+9
+  float a[NA];
 #pragma unroll
-  for (int i = 0; i < 26; ++i) {
+  for (int i = 0; i < NA; ++i) {
     float u;
     if ((i & 1) == 0) {
       // m odd = 2j+1, j = tg-3+i/2 -> xw index of x[j] is j-tg+8 = 5+i/2
@@ -68,25 +77,25 @@ __device__ __forceinline__ void act1d_window(float (&xw)[24], float (&y)[8], flo
       u = fmaf(g3, xw[c + 1], u);
       u = fmaf(g1, xw[c + 2], u);
     }
-    a[i] = snake<PRECISE>(u, ea, ib);
+    a[i] = snake<PRECISE>(u, sc0, sc1);
   }
   // replicate padding of the ACTIVATED signal (F.pad(x,(5,6),'replicate'), filter.py:90-92)
   const int64_t m0 = 2 * tg - 5;
-  if (m0 < 0 || m0 + 25 > 2 * T - 1) {
+  if (m0 < 0 || m0 + NA - 1 > 2 * T - 1) {
     float al = 0.f, ar = 0.f;
 #pragma unroll
-    for (int i = 0; i < 26; ++i) {
+    for (int i = 0; i < NA; ++i) {
       if (m0 + i == 0) al = a[i];
       if (m0 + i == 2 * T - 1) ar = a[i];
     }
 #pragma unroll
-    for (int i = 0; i < 26; ++i) {
+    for (int i = 0; i < NA; ++i) {
       if (m0 + i < 0) a[i] = al;
       if (m0 + i > 2 * T - 1) a[i] = ar;
     }
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < V; ++q) {
     const int i = 2 * q;
     // symmetric taps: f[k] == f[11-k]
     float s = BVG_F0 * (a[i] + a[i + 11]);

@@ -33,7 +33,8 @@ namespace {
 
 constexpr int kXStages = 2;
 constexpr int kWStages = 4;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -83,6 +84,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -96,6 +108,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Persistent kernel: each CTA walks tiles (m_tile, n_block, batch) with a static stride; the smem rings and
+// the TMEM accumulator stages keep flowing across tiles, so the epilogue of tile i overlaps the
+// mainloop of tile i+1 whenever two accumulator stages fit in TMEM.
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -110,20 +125,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   uint64_t* empty_x = full_x + kXStages;
   uint64_t* full_w = empty_x + kXStages;
   uint64_t* empty_w = full_w + kWStages;
-  uint64_t* tmem_full = empty_w + kWStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [NB]
+  uint64_t* tmem_full = empty_w + kWStages;                       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [n_nblk * NB]
 
-  const int tile = blockIdx.x % P.tiles_per_batch;
-  const int b = blockIdx.x / P.tiles_per_batch;
-  const int nb = blockIdx.y;
-  const int q0 = tile * P.MT * 128;                              // first coarse row of this CTA
   const int nacc = P.MT * P.NPH;
+  const int acc_cols = nacc * P.NB;
+  const int ntiles = P.tiles_per_batch * P.n_nblk * P.B;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kXStages; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -131,10 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < P.NB; i += 128) {
-      const int co = nb * P.NB + i;
-      bias_s[i] = (P.bias && co < P.Cout) ? P.bias[co] : 0.f;
-    }
+    for (int i = threadIdx.x - 64; i < P.n_nblk * P.NB; i += kEpiWarps * 32)
+      bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -144,25 +156,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
-      const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;      // first staged row within a chunk
       int xs = 0, ws = 0;
       uint32_t xph = 0, wph = 0;
-      for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-        const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-        mbar_wait(&empty_x[xs], xph ^ 1);
-        mbar_expect_tx(&full_x[xs], (uint32_t)kcn * P.XR * 16u);
-        for (int kc = 0; kc < kcn; ++kc)
-          bulk_g2s(smem_u32(xsm + xs * x_stage_bytes) + kc * P.XR * 16,
-                   xb + ((int64_t)(cb * 8 + kc) * P.x_tp + row_start) * 8, (uint32_t)P.XR * 16u, &full_x[xs]);
-        if (++xs == kXStages) { xs = 0; xph ^= 1; }
-        const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
-        const __nv_bfloat16* wsrc = P.w + ((int64_t)nb * P.Cin_p + (int64_t)cb * 64) * P.NB * P.ntaps;
-        for (int tp = 0; tp < P.ntaps; ++tp) {
-          mbar_wait(&empty_w[ws], wph ^ 1);
-          mbar_expect_tx(&full_w[ws], wbytes);
-          bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
-          if (++ws == kWStages) { ws = 0; wph ^= 1; }
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nb = tile % P.n_nblk;
+        const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
+        const int b = tile / (P.n_nblk * P.tiles_per_batch);
+        const int q0 = mt * P.MT * 128;
+        const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
+        const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;    // first staged row within a chunk
+        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
+          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
+          mbar_wait(&empty_x[xs], xph ^ 1);
+          mbar_expect_tx(&full_x[xs], (uint32_t)kcn * P.XR * 16u);
+          for (int kc = 0; kc < kcn; ++kc)
+            bulk_g2s(smem_u32(xsm + xs * x_stage_bytes) + kc * P.XR * 16,
+                     xb + ((int64_t)(cb * 8 + kc) * P.x_tp + row_start) * 8, (uint32_t)P.XR * 16u, &full_x[xs]);
+          if (++xs == kXStages) { xs = 0; xph ^= 1; }
+          const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
+          const __nv_bfloat16* wsrc = P.w + ((int64_t)nb * P.Cin_p + (int64_t)cb * 64) * P.NB * P.ntaps;
+          for (int tp = 0; tp < P.ntaps; ++tp) {
+            mbar_wait(&empty_w[ws], wph ^ 1);
+            mbar_expect_tx(&full_w[ws], wbytes);
+            bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
+            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+          }
         }
       }
     }
@@ -171,91 +189,129 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = NB, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
-      int xs = 0, ws = 0;
-      uint32_t xph = 0, wph = 0;
-      uint32_t touched = 0;
-      for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-        const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-        mbar_wait(&full_x[xs], xph);
-        const uint32_t xaddr = smem_u32(xsm + xs * x_stage_bytes);
-        for (int tp = 0; tp < P.ntaps; ++tp) {
-          mbar_wait(&full_w[ws], wph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t waddr = smem_u32(wsm + ws * w_stage_bytes);
-          const int shift = P.tap_shift[tp];
-          for (int ms = 0; ms < P.MT; ++ms) {
-            const int acc = ms * P.NPH + P.tap_acc[tp];
-            const uint32_t d = tmem_base + (uint32_t)(acc * P.NB);
-            for (int k2 = 0; k2 < kcn; k2 += 2) {
-              const uint64_t ad = make_desc(xaddr + (uint32_t)((ms * 128 + shift) * 16 + k2 * P.XR * 16), P.XR * 16, 128);
-              const uint64_t bd = make_desc(waddr + (uint32_t)(k2 * P.NB * 16), P.NB * 16, 128);
-              umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
-              touched |= 1u << acc;
+      int xs = 0, ws = 0, as = 0;
+      uint32_t xph = 0, wph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aph ^ 1);                        // epilogue drained this accumulator stage
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dbase = tmem_base + (uint32_t)(as * acc_cols);
+        uint32_t touched = 0;
+        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
+          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
+          mbar_wait(&full_x[xs], xph);
+          const uint32_t xaddr = smem_u32(xsm + xs * x_stage_bytes);
+          for (int tp = 0; tp < P.ntaps; ++tp) {
+            mbar_wait(&full_w[ws], wph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t waddr = smem_u32(wsm + ws * w_stage_bytes);
+            const int shift = P.tap_shift[tp];
+            for (int ms = 0; ms < P.MT; ++ms) {
+              const int acc = ms * P.NPH + P.tap_acc[tp];
+              const uint32_t d = dbase + (uint32_t)(acc * P.NB);
+              for (int k2 = 0; k2 < kcn; k2 += 2) {
+                const uint64_t ad = make_desc(xaddr + (uint32_t)((ms * 128 + shift) * 16 + k2 * P.XR * 16), P.XR * 16, 128);
+                const uint64_t bd = make_desc(waddr + (uint32_t)(k2 * P.NB * 16), P.NB * 16, 128);
+                umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
+                touched |= 1u << acc;
+              }
             }
+            umma_commit(&empty_w[ws]);            // weight slot reusable once these MMAs retire
+            if (++ws == kWStages) { ws = 0; wph ^= 1; }
           }
-          umma_commit(&empty_w[ws]);            // weight slot reusable once these MMAs retire
-          if (++ws == kWStages) { ws = 0; wph ^= 1; }
+          umma_commit(&empty_x[xs]);
+          if (++xs == kXStages) { xs = 0; xph ^= 1; }
         }
-        umma_commit(&empty_x[xs]);
-        if (++xs == kXStages) { xs = 0; xph ^= 1; }
+        umma_commit(&tmem_full[as]);
+        if (++as == P.acc_stages) { as = 0; aph ^= 1; }
       }
-      umma_commit(tmem_full);
     }
   } else {
-    // ===================== epilogue =====================
-    const int wq = warp & 3;                                       // TMEM lane quarter of this warp
+    // ===================== epilogue (kEpiWarps warps: TMEM lane quarter x column half) =====================
+    const int wq = warp & 3;                                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                              // which 32-column groups this warp takes
     const int r = wq * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
-    const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
-    const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
-    const float* cond = P.cond ? P.cond + (int64_t)(P.cond_B == 1 ? 0 : b) * P.Cout : nullptr;
-    for (int a = 0; a < nacc; ++a) {
-      const int ms = a / P.NPH, s = a - ms * P.NPH;
-      const int64_t q = (int64_t)q0 + ms * 128 + r;
-      const int64_t t = q * P.u + s - P.p;
-      const bool valid = (t >= 0) && (t < P.Tout);
-      for (int c0 = 0; c0 < P.NB; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * P.NB + c0), v);
-        if (!valid) continue;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nb = tile % P.n_nblk;
+      const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
+      const int b = tile / (P.n_nblk * P.tiles_per_batch);
+      const int q0 = mt * P.MT * 128;
+      __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
+      const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
+      const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
+      const float* cond = P.cond ? P.cond + (int64_t)(P.cond_B == 1 ? 0 : b) * P.Cout : nullptr;
+      const float* bs = bias_s + nb * P.NB;
+      mbar_wait(&tmem_full[as], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
+      for (int a = 0; a < nacc; ++a) {
+        const int ms = a / P.NPH, s = a - ms * P.NPH;
+        const int64_t q = (int64_t)q0 + ms * 128 + r;
+        const int64_t t = q * P.u + s - P.p;
+        const bool valid = (t >= 0) && (t < P.Tout);
+        const int64_t rowoff = ((int64_t)P.y_row0 + (valid ? t : 0)) * 8;
+        for (int c0 = half * 32; c0 < P.NB; c0 += 64) {
+          // this iteration: columns [c0, c0+32) of accumulator a (the last group may be 16 wide)
+          const int ng = (c0 + 16 < P.NB) ? 4 : 2;                  // 8-channel chunks in this group
+          const int cobase = nb * P.NB + c0;
+          uint4 e1[4], e2[4];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int co = nb * P.NB + c0 + 8 * g;
-          if (co >= P.y_chunks * 8) continue;      // padding channels inside the tensor are written as zeros
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[c0 + 8 * g + j];
-          if (cond) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (co + j < P.Cout) f[j] += cond[co + j];
+          for (int g = 0; g < 4; ++g) {
+            e1[g] = make_uint4(0, 0, 0, 0); e2[g] = make_uint4(0, 0, 0, 0);
+            const int co = cobase + 8 * g;
+            if (valid && g < ng && co < P.y_chunks * 8) {
+              const int64_t off = (int64_t)(co >> 3) * P.y_tp * 8 + rowoff;
+              if (r1) e1[g] = *reinterpret_cast<const uint4*>(r1 + off);
+              if (r2) e2[g] = *reinterpret_cast<const uint4*>(r2 + off);
+            }
           }
-          const int64_t off = ((int64_t)(co >> 3) * P.y_tp + P.y_row0 + t) * 8;
-          if (r1) { float e[8]; unpack8(*reinterpret_cast<const uint4*>(r1 + off), e);
+          uint32_t v[32];
+          tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          if (ng == 4) tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!valid) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
-          if (r2) { float e[8]; unpack8(*reinterpret_cast<const uint4*>(r2 + off), e);
+          for (int g = 0; g < 4; ++g) {
+            const int co = cobase + 8 * g;
+            if (g >= ng || co >= P.y_chunks * 8) continue;           // padding channels inside the tensor are written as zeros
+            float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
-          uint4 o;
-          o.x = pack2(f[0] * P.scale, f[1] * P.scale); o.y = pack2(f[2] * P.scale, f[3] * P.scale);
-          o.z = pack2(f[4] * P.scale, f[5] * P.scale); o.w = pack2(f[6] * P.scale, f[7] * P.scale);
-          *reinterpret_cast<uint4*>(yb + off) = o;
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bs[c0 + 8 * g + j];
+            if (cond) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (co + j < P.Cout) f[j] += cond[co + j];
+            }
+            if (r1) { float e[8]; unpack8(e1[g], e);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += e[j]; }
+            if (r2) { float e[8]; unpack8(e2[g], e);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += e[j]; }
+            uint4 o;
+            o.x = pack2(f[0] * P.scale, f[1] * P.scale); o.y = pack2(f[2] * P.scale, f[3] * P.scale);
+            o.z = pack2(f[4] * P.scale, f[5] * P.scale); o.w = pack2(f[6] * P.scale, f[7] * P.scale);
+            *reinterpret_cast<uint4*>(yb + (int64_t)(co >> 3) * P.y_tp * 8 + rowoff) = o;
+          }
         }
       }
-    }
-    if (P.zero_pads) {
-      // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
-      const int et = threadIdx.x - 64;
-      const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, P.y_chunks - ch0);
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      if (tile == 0)
-        for (int i = et; i < chn * P.y_row0; i += 128)
-          *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
-      if (tile == P.tiles_per_batch - 1)
-        for (int i = et; i < chn * P.y_row0; i += 128)
-          *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
+      // all of this warp's TMEM reads for the stage are complete: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == P.acc_stages) { as = 0; aph ^= 1; }
+      if (P.zero_pads) {
+        // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
+        const int et = threadIdx.x - 64;
+        const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, P.y_chunks - ch0);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (mt == 0)
+          for (int i = et; i < chn * P.y_row0; i += kEpiWarps * 32)
+            *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
+        if (mt == P.tiles_per_batch - 1)
+          for (int i = et; i < chn * P.y_row0; i += kEpiWarps * 32)
+            *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -328,8 +384,9 @@ __global__ void from_c8t_kernel(TD* __restrict__ dst, const __nv_bfloat16* __res
 
 }  // namespace
 
-size_t umma_smem_bytes(int XR, int NB) {
-  return (size_t)kXStages * XR * 128 + (size_t)kWStages * NB * 128 + (2 * kXStages + 2 * kWStages + 1) * 8 + 16 + (size_t)NB * 4 + 128;
+size_t umma_smem_bytes(int XR, int NB, int n_nblk) {
+  return (size_t)kXStages * XR * 128 + (size_t)kWStages * NB * 128 + (2 * kXStages + 2 * kWStages + 4) * 8 + 16 +
+         (size_t)NB * n_nblk * 4 + 128;
 }
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
@@ -406,19 +463,30 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.w = L.w;
   P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
-  int cols = P.MT * P.NPH * P.NB, pw = 32;
+  const int acc_cols = P.MT * P.NPH * P.NB;
+  P.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
+  int cols = acc_cols * P.acc_stages, pw = 32;
   while (pw < cols) pw <<= 1;
   BVG_CHECK_ARG(pw <= 512, "conv_umma: accumulators exceed TMEM");
   P.tmem_cols = pw;
-  const size_t smem = umma_smem_bytes(P.XR, P.NB);
+  P.n_nblk = n_nblk;
+  P.B = (int)B;
+  const size_t smem = umma_smem_bytes(P.XR, P.NB, n_nblk);
   BVG_CHECK_ARG(smem <= 227 * 1024, "conv_umma: tile needs %zu B of shared memory", smem);
   static bool attr_set = false;
   if (!attr_set) {
     BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  BVG_CHECK_ARG((int64_t)P.tiles_per_batch * B < (1ll << 31), "conv_umma: grid too large");
-  dim3 grid((unsigned)(P.tiles_per_batch * B), (unsigned)n_nblk);
+  const int64_t ntiles = (int64_t)P.tiles_per_batch * B * n_nblk;
+  BVG_CHECK_ARG(ntiles < (1ll << 31), "conv_umma: too many tiles");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    BVG_CUDA(cudaGetDevice(&dev));
+    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
   ProfScope prof(st, L.transposed ? KC_CONVTR : KC_CONV);
   conv_umma_kernel<<<grid, kThreads, smem, st>>>(P);
   BVG_LAUNCHED();

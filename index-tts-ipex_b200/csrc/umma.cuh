@@ -52,9 +52,10 @@ struct UmmaConvParams {
   int ntaps; int16_t tap_shift[16]; int16_t tap_acc[16];
   int lo, XR;                         // staged rows: [q0 - lo, q0 - lo + XR)
   int n_ci_blk, Cin_p, NB, Cout, NPH, MT, tiles_per_batch, zero_pads, tmem_cols;
+  int acc_stages, n_nblk, B;
 };
 
-size_t umma_smem_bytes(int XR, int NB);
+size_t umma_smem_bytes(int XR, int NB, int n_nblk);
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
 int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
