@@ -109,6 +109,10 @@ BVG_API int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, co
  * converts internally; test entry point). */
 BVG_API int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                       int64_t B, int64_t C, int64_t T, void* stream);
+/* Profiling aid: when non-NULL, the next bvg_conv*_umma_fwd launches write 8 int64 cycle counters per CTA
+ * (148 CTAs max) into this device buffer: producer wait, MMA waits on input / weights / TMEM, MMA issue,
+ * MMA-thread total, epilogue wait, epilogue busy. */
+BVG_API void bvg_debug_set_umma_counters(long long* dev_buf);
 BVG_API int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
                         const void* res1, const void* res2, float scale,
                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);

@@ -21,6 +21,7 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (one per TMEM lane quarter).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,10 +32,12 @@
 namespace bvg {
 namespace {
 
-constexpr int kXStages = 2;
-constexpr int kWStages = 4;
+constexpr int kMaxXStages = 4;
+constexpr int kMaxWStages = 32;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kMaxIssuers = 4;                         // MMA-issuing warps (one tcgen05.mma stream each)
+constexpr int kEpiWarp0 = 1 + kMaxIssuers;             // first epilogue warp (kEpiWarp0 % 4 == 1)
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -95,6 +98,54 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one elected lane of a fully converged warp (CUTLASS elect_one_sync): keeps the surrounding control flow
+// warp-uniform, so descriptors live in uniform registers and tcgen05.mma needs no per-lane serialisation
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// D[tmem] (+)= A * B with the descriptors given as (lo, shared hi) words; executed by one elected lane of a
+// converged warp, all operands warp-uniform
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, e;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// single-thread form: descriptor hi word (SBO = 128 B, version 1, no swizzle) is an immediate, so only the two
+// lo words and the accumulator address change between MMAs
+__device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, 0x4008};\nmov.b64 db, {%2, 0x4008};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// NK back-to-back MMAs along K (one per 16 input channels), fully unrolled so that every MMA gets its own
+// uniform registers for the two descriptors and the issue does not serialise on them
+template <int NK>
+__device__ __forceinline__ void issue_k(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum,
+                                        uint32_t astep, uint32_t bstep) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    umma_bf16(d, ad + (uint64_t)(k * astep), bd + (uint64_t)(k * bstep), idesc, k ? 1u : accum);
+  }
+}
+
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -108,6 +159,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// optional per-role cycle accounting (UmmaConvParams::dbg != nullptr): 8 counters per CTA
+#define DBG_T0() const long long dbg_t0__ = P.dbg ? clock64() : 0
+#define DBG_ADD(var) do { if (P.dbg) (var) += clock64() - dbg_t0__; } while (0)
+
 // Persistent kernel: each CTA walks tiles (m_tile, n_block, batch) with a static stride; the smem rings and
 // the TMEM accumulator stages keep flowing across tiles, so the epilogue of tile i overlaps the
 // mainloop of tile i+1 whenever two accumulator stages fit in TMEM.
@@ -116,16 +171,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const uint32_t x_stage_bytes = (uint32_t)P.XR * 128u;          // 8 kchunks x XR rows x 16 B
-  const uint32_t w_stage_bytes = (uint32_t)P.NB * 128u;          // 8 kchunks x NB rows x 16 B
+  const int kXStages = P.x_stages, kWStages = P.w_stages;
+  const uint32_t x_stage_bytes = (uint32_t)P.XR * P.kc_max * 16u;  // kc_max kchunks x XR rows x 16 B
+  const uint32_t w_stage_bytes = (uint32_t)P.NB * P.kc_max * 16u;  // kc_max kchunks x NB rows x 16 B
   uint8_t* xsm = smem;
   uint8_t* wsm = smem + kXStages * x_stage_bytes;
   uint8_t* tail = wsm + kWStages * w_stage_bytes;
   uint64_t* full_x = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_x = full_x + kXStages;
-  uint64_t* full_w = empty_x + kXStages;
-  uint64_t* empty_w = full_w + kWStages;
-  uint64_t* tmem_full = empty_w + kWStages;                       // [2]
+  uint64_t* empty_x = full_x + kMaxXStages;
+  uint64_t* full_w = empty_x + kMaxXStages;
+  uint64_t* empty_w = full_w + kMaxWStages;
+  uint64_t* tmem_full = empty_w + kMaxWStages;                    // [2]
   uint64_t* tmem_empty = tmem_full + 2;                           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [n_nblk * NB]
@@ -135,17 +191,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   const int ntiles = P.tiles_per_batch * P.n_nblk * P.B;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kXStages; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], 1); }
-    for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&full_x[i], 1); mbar_init(&empty_x[i], P.n_issuers); }
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], P.n_issuers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], P.n_issuers); mbar_init(&tmem_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(P.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < P.n_nblk * P.NB; i += kEpiWarps * 32)
+  if (warp >= kEpiWarp0) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.n_nblk * P.NB; i += kEpiWarps * 32)
       bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -155,9 +211,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !P.dry) {
       int xs = 0, ws = 0;
       uint32_t xph = 0, wph = 0;
+      long long dbg_prod_wait = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nb = tile % P.n_nblk;
         const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
@@ -167,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
         const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;    // first staged row within a chunk
         for (int cb = 0; cb < P.n_ci_blk; ++cb) {
           const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-          mbar_wait(&empty_x[xs], xph ^ 1);
+          { DBG_T0(); mbar_wait(&empty_x[xs], xph ^ 1); DBG_ADD(dbg_prod_wait); }
           mbar_expect_tx(&full_x[xs], (uint32_t)kcn * P.XR * 16u);
           for (int kc = 0; kc < kcn; ++kc)
             bulk_g2s(smem_u32(xsm + xs * x_stage_bytes) + kc * P.XR * 16,
@@ -175,64 +232,131 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           if (++xs == kXStages) { xs = 0; xph ^= 1; }
           const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
           const __nv_bfloat16* wsrc = P.w + ((int64_t)nb * P.Cin_p + (int64_t)cb * 64) * P.NB * P.ntaps;
-          for (int tp = 0; tp < P.ntaps; ++tp) {
-            mbar_wait(&empty_w[ws], wph ^ 1);
-            mbar_expect_tx(&full_w[ws], wbytes);
-            bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
-            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+          if (P.w_resident) {
+            // the whole layer's weights stay in shared memory: fetched once, on this CTA's first tile
+            if (tile == (int)blockIdx.x)
+              for (int tp = 0; tp < P.ntaps; ++tp) {
+                const int slot = cb * P.ntaps + tp;
+                mbar_expect_tx(&full_w[slot], wbytes);
+                bulk_g2s(smem_u32(wsm + slot * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[slot]);
+              }
+          } else {
+            for (int tp = 0; tp < P.ntaps; ++tp) {
+              { DBG_T0(); mbar_wait(&empty_w[ws], wph ^ 1); DBG_ADD(dbg_prod_wait); }
+              mbar_expect_tx(&full_w[ws], wbytes);
+              bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
+              if (++ws == kWStages) { ws = 0; wph ^= 1; }
+            }
           }
         }
       }
+      if (P.dbg) P.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait;
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp < kEpiWarp0) {
+    // ===================== MMA issuers =====================
+    // A single warp sustains roughly one tcgen05.mma per ~100 cycles, twice the execution time of a narrow
+    // (N <= 96) MMA, so the accumulators are dealt out to n_issuers warps: issuer ii owns accumulators
+    // acc % n_issuers == ii and runs its own tcgen05.mma / tcgen05.commit stream; every ring barrier that the
+    // MMAs release therefore expects n_issuers arrivals.
+    // The whole warp runs this loop with warp-uniform values (descriptor words stay in uniform registers and
+    // advance with uniform adds); only the tcgen05.mma / tcgen05.commit instructions sit under elect_one.
+    // The issue path between two MMAs must stay well under the ~54-cycle execution time of a small-N MMA.
+    const int ii = warp - 1;
+    if (ii < P.n_issuers) {
+      // Everything the loop needs is pinned in registers (the empty asm hides the values from constant
+      // re-materialisation): a kernel-parameter reload (LDCU) between two MMAs costs more than a narrow MMA takes.
+#define PIN(v) asm volatile("" : "+r"(v))
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = NB, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
+      uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
+      // smem descriptors (K-major, no swizzle): lo word = start>>4 | (LBO>>4)<<16, hi word = SBO>>4 | version
+      uint32_t a_lbo = (uint32_t)P.XR << 16, b_lbo = (uint32_t)P.NB << 16;
+      uint32_t astep = 2u * P.XR, bstep = 2u * P.NB;                 // 16 input channels further along K
+      int NB = P.NB, MT = P.MT, NPH = P.NPH, dil = P.dil, n_iss = P.n_issuers, ntaps = P.ntaps;
+      int n_ci_blk = P.n_ci_blk, Cin_p = P.Cin_p, resident = P.w_resident, dry = P.dry, transposed = P.transposed;
+      int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols;
+      uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
+      uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
+      PIN(idesc); PIN(astep); PIN(bstep); PIN(NB); PIN(MT); PIN(NPH); PIN(dil); PIN(n_iss); PIN(ntaps);
+      PIN(n_ci_blk); PIN(Cin_p); PIN(resident); PIN(dry); PIN(transposed); PIN(n_xst); PIN(n_wst); PIN(n_ast);
+      PIN(acols); PIN(xsb16); PIN(wslot16); PIN(x_base); PIN(w_base);
+#undef PIN
+      const int first_tile = blockIdx.x;
       int xs = 0, ws = 0, as = 0;
       uint32_t xph = 0, wph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aph ^ 1);                        // epilogue drained this accumulator stage
+      long long dbg_wx = 0, dbg_ww = 0, dbg_wt = 0, dbg_issue = 0;   // (dbg_issue spans a whole channel block, weight waits included)
+      const long long dbg_start = P.dbg ? clock64() : 0;
+      for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
+        if (!dry) { DBG_T0(); mbar_wait(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }   // epilogue drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dbase = tmem_base + (uint32_t)(as * acc_cols);
-        uint32_t touched = 0;
-        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-          mbar_wait(&full_x[xs], xph);
-          const uint32_t xaddr = smem_u32(xsm + xs * x_stage_bytes);
-          for (int tp = 0; tp < P.ntaps; ++tp) {
-            mbar_wait(&full_w[ws], wph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t waddr = smem_u32(wsm + ws * w_stage_bytes);
-            const int shift = P.tap_shift[tp];
-            for (int ms = 0; ms < P.MT; ++ms) {
-              const int acc = ms * P.NPH + P.tap_acc[tp];
-              const uint32_t d = dbase + (uint32_t)(acc * P.NB);
-              for (int k2 = 0; k2 < kcn; k2 += 2) {
-                const uint64_t ad = make_desc(xaddr + (uint32_t)((ms * 128 + shift) * 16 + k2 * P.XR * 16), P.XR * 16, 128);
-                const uint64_t bd = make_desc(waddr + (uint32_t)(k2 * P.NB * 16), P.NB * 16, 128);
-                umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
-                touched |= 1u << acc;
+        const uint32_t dbase = tmem_base + (uint32_t)(as * acols);
+        for (int cb = 0; cb < n_ci_blk; ++cb) {
+          const int nk = min(8, (Cin_p - cb * 64) >> 3) >> 1;       // MMAs along K in this channel block (1..4)
+          if (!dry) { DBG_T0(); mbar_wait(&full_x[xs], xph); DBG_ADD(dbg_wx); }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          DBG_T0();
+          const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
+          for (int tp = 0; tp < ntaps; ++tp) {
+            const int slot = resident ? cb * ntaps + tp : ws;
+            if (!dry && (!resident || tile == first_tile)) {        // resident weights are waited for once
+              mbar_wait(&full_w[slot], resident ? 0u : wph);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
+            const uint32_t accum0 = (cb > 0 || tp >= NPH) ? 1u : 0u;  // taps 0..NPH-1 are the first to touch their accumulator
+            if (lane == 0) {
+              if (!transposed) {
+                // conv: tap = row shift tp*dil; issuer ii owns time sub-tiles ms = ii, ii + n_issuers, ...
+                const uint32_t a_tp = a_cb + (uint32_t)(tp * dil);
+                for (int ms = ii; ms < MT; ms += n_iss) {
+                  const uint32_t d = dbase + (uint32_t)(ms * NB);
+                  uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
+                  umma_bf16_imm(d, am, bm, idesc, accum0);
+                  for (int k = 1; k < nk; ++k) {
+                    am += astep; bm += bstep;
+                    umma_bf16_imm(d, am, bm, idesc, 1u);
+                  }
+                }
+              } else if ((P.tap_acc[tp] & (n_iss - 1)) == ii) {
+                // ConvTranspose: one accumulator per output phase, issuer ii owns phases == ii (mod n_issuers)
+                const uint32_t d = dbase + (uint32_t)(P.tap_acc[tp] * NB);
+                uint32_t am = a_cb + (uint32_t)P.tap_shift[tp], bm = b_lo;
+                umma_bf16_imm(d, am, bm, idesc, accum0);
+                for (int k = 1; k < nk; ++k) {
+                  am += astep; bm += bstep;
+                  umma_bf16_imm(d, am, bm, idesc, 1u);
+                }
               }
             }
-            umma_commit(&empty_w[ws]);            // weight slot reusable once these MMAs retire
-            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+            if (!resident && !dry) {
+              umma_commit_elect(&empty_w[ws]);        // weight slot reusable once these MMAs retire
+              if (++ws == n_wst) { ws = 0; wph ^= 1; }
+            }
           }
-          umma_commit(&empty_x[xs]);
-          if (++xs == kXStages) { xs = 0; xph ^= 1; }
+          DBG_ADD(dbg_issue);
+          if (!dry) umma_commit_elect(&empty_x[xs]);
+          if (++xs == n_xst) { xs = 0; xph ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
-        if (++as == P.acc_stages) { as = 0; aph ^= 1; }
+        if (!dry) umma_commit_elect(&tmem_full[as]);
+        if (++as == n_ast) { as = 0; aph ^= 1; }
+      }
+      if (dry) {                         // drain: wait for every issued MMA so the total is inclusive
+        umma_commit_elect(&tmem_full[0]);
+        mbar_wait(&tmem_full[0], 0);
+      }
+      if (P.dbg && lane == 0 && ii == 0) {
+        long long* d = P.dbg + blockIdx.x * 8;
+        d[1] = dbg_wx; d[2] = dbg_ww; d[3] = dbg_wt; d[4] = dbg_issue; d[5] = clock64() - dbg_start;
       }
     }
   } else {
     // ===================== epilogue (kEpiWarps warps: TMEM lane quarter x column half) =====================
     const int wq = warp & 3;                                       // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                              // which 32-column groups this warp takes
+    const int half = (warp - kEpiWarp0) >> 2;                      // which 32-column groups this warp takes
     const int r = wq * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long dbg_ewait = 0, dbg_ebusy = 0;
+    for (int tile = blockIdx.x; tile < (P.dry ? 0 : ntiles); tile += gridDim.x) {
       const int nb = tile % P.n_nblk;
       const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
       const int b = tile / (P.n_nblk * P.tiles_per_batch);
@@ -242,17 +366,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
       const float* cond = P.cond ? P.cond + (int64_t)(P.cond_B == 1 ? 0 : b) * P.Cout : nullptr;
       const float* bs = bias_s + nb * P.NB;
-      mbar_wait(&tmem_full[as], aph);
+      { DBG_T0(); mbar_wait(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      DBG_T0();
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
-      for (int a = 0; a < nacc; ++a) {
+      // work items = (accumulator, 32-column group); the two warps of a TMEM lane quarter take alternate items
+      const int ngrp = (P.NB + 31) >> 5;
+      for (int item = half; item < nacc * ngrp; item += 2) {
+        const int a = item / ngrp, c0 = (item - a * ngrp) << 5;
         const int ms = a / P.NPH, s = a - ms * P.NPH;
         const int64_t q = (int64_t)q0 + ms * 128 + r;
         const int64_t t = q * P.u + s - P.p;
         const bool valid = (t >= 0) && (t < P.Tout);
         const int64_t rowoff = ((int64_t)P.y_row0 + (valid ? t : 0)) * 8;
-        for (int c0 = half * 32; c0 < P.NB; c0 += 64) {
-          // this iteration: columns [c0, c0+32) of accumulator a (the last group may be 16 wide)
+        {
+          // columns [c0, c0+32) of accumulator a (the last group may be 16 wide)
           const int ng = (c0 + 16 < P.NB) ? 4 : 2;                  // 8-channel chunks in this group
           const int cobase = nb * P.NB + c0;
           uint4 e1[4], e2[4];
@@ -299,10 +427,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      DBG_ADD(dbg_ebusy);
       if (++as == P.acc_stages) { as = 0; aph ^= 1; }
       if (P.zero_pads) {
         // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
-        const int et = threadIdx.x - 64;
+        const int et = threadIdx.x - kEpiWarp0 * 32;
         const int ch0 = (nb * P.NB) >> 3, chn = min(P.NB >> 3, P.y_chunks - ch0);
         const uint4 z = make_uint4(0, 0, 0, 0);
         if (mt == 0)
@@ -313,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
       }
     }
+    if (P.dbg && threadIdx.x == kEpiWarp0 * 32) { P.dbg[blockIdx.x * 8 + 6] = dbg_ewait; P.dbg[blockIdx.x * 8 + 7] = dbg_ebusy; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -384,9 +514,8 @@ __global__ void from_c8t_kernel(TD* __restrict__ dst, const __nv_bfloat16* __res
 
 }  // namespace
 
-size_t umma_smem_bytes(int XR, int NB, int n_nblk) {
-  return (size_t)kXStages * XR * 128 + (size_t)kWStages * NB * 128 + (2 * kXStages + 2 * kWStages + 4) * 8 + 16 +
-         (size_t)NB * n_nblk * 4 + 128;
+static size_t umma_fixed_smem(int NB, int n_nblk) {
+  return (size_t)(2 * kMaxXStages + 2 * kMaxWStages + 4) * 8 + 16 + (size_t)NB * n_nblk * 4 + 128;
 }
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
@@ -429,7 +558,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   umma_choose_nb(L.Cout, P.NPH, &P.NB, &n_nblk);
   P.ntaps = L.K;
   BVG_CHECK_ARG(L.K <= 16, "conv_umma: at most 16 taps");
-  P.MT = (P.NPH * P.NB * 2 <= 512 && !L.transposed) ? 2 : 1;
+  // time sub-tiles per CTA: every weight tile is shared by MT*128 output rows
+  P.MT = L.transposed ? 1 : (P.NB <= 64 ? 4 : 2);
   int halo;
   if (!L.transposed) {
     BVG_CHECK_ARG(y.T == x.T, "conv_umma: conv keeps the length");
@@ -463,6 +593,10 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.w = L.w;
   P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
+  P.dbg = ep.dbg;
+  P.dry = ep.dry;
+  P.transposed = L.transposed;
+  P.dil = L.dil;
   const int acc_cols = P.MT * P.NPH * P.NB;
   P.acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
   int cols = acc_cols * P.acc_stages, pw = 32;
@@ -471,8 +605,26 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.tmem_cols = pw;
   P.n_nblk = n_nblk;
   P.B = (int)B;
-  const size_t smem = umma_smem_bytes(P.XR, P.NB, n_nblk);
-  BVG_CHECK_ARG(smem <= 227 * 1024, "conv_umma: tile needs %zu B of shared memory", smem);
+  P.n_issuers = 1;
+  while (P.n_issuers * 2 <= std::min(kMaxIssuers, P.MT * P.NPH)) P.n_issuers *= 2;   // power of two
+  if (const char* e = getenv("BVG_UMMA_ISSUERS")) P.n_issuers = std::max(1, std::min(P.n_issuers, atoi(e)));
+  // shared-memory plan: keep the whole layer's weights resident when they fit next to >= 2 input stages,
+  // otherwise stream them through as deep a ring as fits
+  P.kc_max = std::min(8, P.Cin_p / 8);
+  const size_t budget = 227 * 1024 - umma_fixed_smem(P.NB, n_nblk);
+  const size_t xsb = (size_t)P.XR * P.kc_max * 16, wsb = (size_t)P.NB * P.kc_max * 16;
+  const int wslots = P.ntaps * P.n_ci_blk;
+  BVG_CHECK_ARG(2 * xsb + 2 * wsb <= budget, "conv_umma: tile does not fit shared memory");
+  if (n_nblk == 1 && wslots <= kMaxWStages && wslots * wsb + 2 * xsb <= budget) {
+    P.w_resident = 1;
+    P.w_stages = wslots;
+    P.x_stages = (int)std::min<size_t>(kMaxXStages, (budget - wslots * wsb) / xsb);
+  } else {
+    P.w_resident = 0;
+    P.x_stages = 2;
+    P.w_stages = (int)std::min<size_t>(kMaxWStages, (budget - 2 * xsb) / wsb);
+  }
+  const size_t smem = (size_t)P.x_stages * xsb + (size_t)P.w_stages * wsb + umma_fixed_smem(P.NB, n_nblk);
   static bool attr_set = false;
   if (!attr_set) {
     BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -6,6 +6,7 @@
 // (models.py:201-250) on the caller's stream: ECAPA speaker encoder -> conv_pre + cond ->
 // 6 x (ConvTranspose1d + cond + mean of 3 AMPBlock1) -> Activation1d -> conv_post -> tanh.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -522,6 +523,14 @@ int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, const floa
   return rc;
 }
 
+static long long* g_umma_dbg = nullptr;   // set by bvg_debug_set_umma_counters (profiling only)
+static int g_umma_dry = 0;
+void bvg_debug_set_umma_counters(long long* dev_buf) {
+  g_umma_dbg = dev_buf;
+  const char* e = getenv("BVG_UMMA_DRY");          // profiling only: issue-loop-only dry run (results are garbage)
+  g_umma_dry = (dev_buf && e && e[0] == '1') ? 1 : 0;
+}
+
 static int umma_layer_test(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
                            const void* res2, float scale, const float* cond, int64_t Bc, int64_t B, int64_t Cin,
                            int64_t Cout, int64_t Tin, int K, int dil, int transposed, int stride, cudaStream_t st) {
@@ -548,6 +557,8 @@ static int umma_layer_test(void* dst, const void* src, const float* weight, cons
     UmmaEpilogue ep;
     ep.bias = bias; ep.cond = cond; ep.cond_B = Bc; ep.scale = scale;
     ep.res1 = res1 ? r1.p : nullptr; ep.res2 = res2 ? r2.p : nullptr;
+    ep.dbg = g_umma_dbg;
+    ep.dry = g_umma_dry;
     rc = conv_umma_launch(L, x, y, ep, B, st);
   }
   if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);

@@ -39,6 +39,8 @@ struct UmmaEpilogue {
   const __nv_bfloat16* res2 = nullptr;
   float scale = 1.f;
   int zero_pads = 0;                  // also (re)write the output's zero halo rows
+  int dry = 0;                        // debug: run only the MMA issue loop (no TMA, waits or epilogue)
+  long long* dbg = nullptr;           // optional [grid][8] cycle counters (profiling builds of the tests)
 };
 
 struct UmmaConvParams {
@@ -53,9 +55,13 @@ struct UmmaConvParams {
   int lo, XR;                         // staged rows: [q0 - lo, q0 - lo + XR)
   int n_ci_blk, Cin_p, NB, Cout, NPH, MT, tiles_per_batch, zero_pads, tmem_cols;
   int acc_stages, n_nblk, B;
+  int x_stages, w_stages, w_resident, kc_max;
+  long long* dbg;
+  int dry;
+  int n_issuers;
+  int transposed, dil;
 };
 
-size_t umma_smem_bytes(int XR, int NB, int n_nblk);
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
 int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
