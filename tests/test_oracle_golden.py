@@ -99,3 +99,41 @@ def test_schema_counts():
     assert abs(n - 133.9e6) / 133.9e6 < 0.01
     folded = O.fold_weight_norm({k: torch.zeros(s) + 1 for k, s, _ in sch})
     assert len(folded) == 913
+
+
+def _c_oracle():
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "oracle", "act1d_oracle.c")
+    out = os.path.join(root, "oracle", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libact1d_oracle.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src, "-lm"])
+    lib = ctypes.CDLL(so)
+    lib.act1d_oracle.restype = ctypes.c_int
+    return lib
+
+
+@pytest.mark.parametrize("T", [1, 2, 5, 6, 12, 13, 33, 257, 4097])
+def test_c_restatement_vs_reference_and_closed_form(golden_dir, T):
+    """The plain-C oracle materialises the padded / upsampled signals like the PyTorch ops; it must agree
+    with the reference golden and with the polyphase closed form (two independent restatements)."""
+    import ctypes
+    g = _load(golden_dir, "act1d_cases")
+    lib = _c_oracle()
+    x = g[f"T{T}.x"].astype(np.float64)
+    a = g[f"T{T}.alpha"].astype(np.float64)
+    b = g[f"T{T}.beta"].astype(np.float64)
+    taps = O.act1d_taps()
+    dp = ctypes.POINTER(ctypes.c_double)
+    for bi in range(x.shape[0]):
+        xc = np.ascontiguousarray(x[bi])
+        y = np.empty_like(xc)
+        rc = lib.act1d_oracle(xc.ctypes.data_as(dp), y.ctypes.data_as(dp), a.ctypes.data_as(dp), b.ctypes.data_as(dp),
+                              taps.ctypes.data_as(dp), xc.shape[0], xc.shape[1])
+        assert rc == 0
+        np.testing.assert_allclose(y, g[f"T{T}.y"][bi], rtol=0, atol=2e-6)
+        ref = O.act1d(torch.from_numpy(xc)[None], torch.from_numpy(a), torch.from_numpy(b))[0].numpy()
+        np.testing.assert_allclose(y, ref, rtol=0, atol=1e-12)
