@@ -108,4 +108,71 @@ __device__ __forceinline__ void act1d_window(float (&xw)[V + 16], float (&y)[V],
   }
 }
 
+// ---- two channels at once on packed fp32x2 math (FFMA2 / FADD2 / FMUL2, sm_100+) ----------------------------
+// The stencil is issue-bound on scalar fp32 (about 58 issue slots per sample); a thread of the c8t kernel owns
+// two channels with identical instruction streams, so every FIR multiply-add pairs up across the channels and
+// the slot count halves.  Interior threads only (no replicate padding in the window); results are bit-identical
+// to the scalar path (same operation order; the down-FIR uses the x2 taps and a final exact *0.5).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float x, float y) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y)); return d; }
+__device__ __forceinline__ void unpk2(f32x2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// bf16x2 word (lo = channel A, hi = channel B) -> (float A, float B)
+__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+// wd[j] = packed row tg-8+j of the two channels (j = 0..V+15); outw[q] = packed output row tg+q.
+// sc0 = (2 e^alphaA, 2 e^alphaB), sc1 = (hbA, hbB), nsc1 = -sc1  (fast snake, see snake<false>).
+template <int V>
+__device__ __forceinline__ void act1d_window2(const uint32_t (&wd)[V + 16], uint32_t (&outw)[V], f32x2 sc0, f32x2 sc1,
+                                              f32x2 nsc1) {
+  const f32x2 g0 = pk2(2.f * BVG_F0, 2.f * BVG_F0), g1 = pk2(2.f * BVG_F1, 2.f * BVG_F1),
+              g2 = pk2(2.f * BVG_F2, 2.f * BVG_F2), g3 = pk2(2.f * BVG_F3, 2.f * BVG_F3),
+              g4 = pk2(2.f * BVG_F4, 2.f * BVG_F4), g5 = pk2(2.f * BVG_F5, 2.f * BVG_F5);
+  const f32x2 half = pk2(0.5f, 0.5f);
+  f32x2 X[V + 16];      // unpacked rows (only p+3..p+8 are live around intermediate pair p)
+  f32x2 a[2 * V + 10];  // activated intermediates, a[i] <-> m = 2*tg - 5 + i (12 live at a time)
+#pragma unroll
+  for (int j = 3; j < 8; ++j) X[j] = unpack_bf16x2(wd[j]);
+#pragma unroll
+  for (int p = 0; p < V + 5; ++p) {
+    X[p + 8] = unpack_bf16x2(wd[p + 8]);
+    // i = 2p (m odd):  g1 x[c-2] + g3 x[c-1] + g5 x[c] + g4 x[c+1] + g2 x[c+2] + g0 x[c+3], c = 5+p
+    f32x2 u = mul2(g1, X[p + 3]);
+    u = fma2(g3, X[p + 4], u);
+    u = fma2(g5, X[p + 5], u);
+    u = fma2(g4, X[p + 6], u);
+    u = fma2(g2, X[p + 7], u);
+    u = fma2(g0, X[p + 8], u);
+    // i = 2p+1 (m even): g0 x[c-3] + g2 x[c-2] + g4 x[c-1] + g5 x[c] + g3 x[c+1] + g1 x[c+2], c = 6+p
+    f32x2 w = mul2(g0, X[p + 3]);
+    w = fma2(g2, X[p + 4], w);
+    w = fma2(g4, X[p + 5], w);
+    w = fma2(g5, X[p + 6], w);
+    w = fma2(g3, X[p + 7], w);
+    w = fma2(g1, X[p + 8], w);
+    {
+      float zx, zy;
+      unpk2(mul2(u, sc0), zx, zy);
+      a[2 * p] = fma2(nsc1, pk2(__cosf(zx), __cosf(zy)), add2(u, sc1));
+      unpk2(mul2(w, sc0), zx, zy);
+      a[2 * p + 1] = fma2(nsc1, pk2(__cosf(zx), __cosf(zy)), add2(w, sc1));
+    }
+    if (p >= 5) {
+      const int i = 2 * (p - 5);
+      f32x2 s = mul2(g0, add2(a[i], a[i + 11]));
+      s = fma2(g1, add2(a[i + 1], a[i + 10]), s);
+      s = fma2(g2, add2(a[i + 2], a[i + 9]), s);
+      s = fma2(g3, add2(a[i + 3], a[i + 8]), s);
+      s = fma2(g4, add2(a[i + 4], a[i + 7]), s);
+      s = fma2(g5, add2(a[i + 5], a[i + 6]), s);
+      float yx, yy;
+      unpk2(mul2(s, half), yx, yy);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(yx, yy);
+      outw[p - 5] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+  }
+}
+
 }  // namespace bvg

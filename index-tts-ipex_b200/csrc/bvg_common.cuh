@@ -115,6 +115,9 @@ int repack_conv_weight_launch(float* dst, const float* src, int64_t Cout, int64_
 
 
 // ---- small kernels (misc.cu) ------------------------------------------------------------------
+// y[b,co] = epilogue(sum_ci w[ci][co] x[b,ci]) for contiguous x [B,Cin], y [B,Cout]; w is the K=1 [Cin][Cout] pack
+int matvec_launch(float* y, const float* x, const float* w_ic, const ConvEpilogue& ep, int64_t B, int Cin, int Cout,
+                  cudaStream_t st);
 // mean over time of each row of x [rows, T] (row r at x + r*T) -> out[r]
 int row_mean_launch(float* out, const float* x, int64_t rows, int64_t T, cudaStream_t st);
 // mean/std over time: x [B,C,T] -> ms[b, c] = mean, ms[b, C + c] = sqrt(clamp(var, 1e-12))

@@ -83,6 +83,38 @@ __global__ void attn_stats_kernel(float* __restrict__ pooled, const float* __res
   }
 }
 
+// y[b, co] = epilogue(sum_ci w[ci][co] * x[b, ci]): the T == 1 "convs" of the path (cond vectors, SE block,
+// attentive-statistics context, final fc).  256 threads = 64 outputs x 4 input slices; weights are read
+// coalesced along co from the [Cin][Cout] pack, partial sums meet in shared memory.
+__global__ void __launch_bounds__(256)
+matvec_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ w,
+              const float* __restrict__ bias, int relu, const float* __restrict__ post_scale,
+              const float* __restrict__ post_shift, int act, int Cin, int Cout) {
+  __shared__ float part[4][64];
+  const int co = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int sl = threadIdx.x >> 6;
+  const int b = blockIdx.y;
+  const float* xb = x + (int64_t)b * Cin;
+  float acc = 0.f;
+  if (co < Cout) {
+    const int per = (Cin + 3) / 4;
+    const int lo = sl * per, hi = min(Cin, lo + per);
+#pragma unroll 4
+    for (int ci = lo; ci < hi; ++ci) acc = fmaf(w[(int64_t)ci * Cout + co], xb[ci], acc);
+  }
+  part[sl][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (sl == 0 && co < Cout) {
+    float v = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+    if (bias) v += bias[co];
+    if (relu) v = fmaxf(v, 0.f);
+    if (post_scale) v = fmaf(v, post_scale[co], post_shift[co]);
+    if (act == 1) v = tanhf(v);
+    if (act == 2) v = 1.f / (1.f + expf(-v));
+    y[(int64_t)b * Cout + co] = v;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_post_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const T* __restrict__ x,
@@ -116,6 +148,19 @@ conv_post_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const T* __
 }
 
 }  // namespace
+
+int matvec_launch(float* y, const float* x, const float* w_ic, const ConvEpilogue& ep, int64_t B, int Cin, int Cout,
+                  cudaStream_t st) {
+  BVG_CHECK_ARG(y && x && w_ic && Cin > 0 && Cout > 0, "matvec: bad argument");
+  BVG_CHECK_ARG(!ep.res1 && !ep.res2 && !ep.cond && ep.scale == 1.f, "matvec: unsupported epilogue");
+  if (B == 0) return BVG_OK;
+  BVG_CHECK_ARG(B <= 65535, "matvec: batch too large");
+  dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  matvec_kernel<<<grid, 256, 0, st>>>(y, x, w_ic, ep.bias, ep.relu, ep.post_scale, ep.post_shift, ep.act, Cin, Cout);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
 
 int row_mean_launch(float* out, const float* x, int64_t rows, int64_t T, cudaStream_t st) {
   if (rows == 0) return BVG_OK;

@@ -271,6 +271,9 @@ void carve_ecapa(Bump& b, int64_t Bm, int64_t Tm, EcapaWs* w) {
 int conv_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64_t sb, int64_t sc, int64_t st_,
              const ConvLayer& L, ConvEpilogue ep, int64_t B, int64_t T, int dil, int pad_mode, cudaStream_t st) {
   ep.bias = L.bias;
+  // the T == 1 layers (cond vectors, SE, attentive-statistics context, fc) are matrix-vector products
+  if (T == 1 && L.K == 1 && !src2 && sc == 1 && sb == L.Cin && dsb == L.Cout && !ep.cond && !ep.res1 && !ep.res2)
+    return matvec_launch(dst, src, L.w, ep, B, L.Cin, L.Cout, st);
   return conv1d_simt_launch(dst, dsb, src, src2, sb, sc, st_, L.w, ep, B, L.Cin, L.Cout, T, L.K, dil, pad_mode,
                             BVG_F32, BVG_F32, st);
 }
