@@ -95,15 +95,15 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
     // interior: both channels real, no replicate padding inside the window -> packed fp32x2 fast path
     const bool interior = (t0 - 5 >= 0) && (t0 + V + 4 <= T - 1) && (chA + 1 < C);
     if (interior) {
-      uint32_t wd[V + 16], ow[V];
+      uint32_t wd[V + 16];
 #pragma unroll
       for (int j = 3; j < V + 13; ++j) wd[j] = inw[j * 4];
       float a0, b0, a1, b1;
       snake_params<false>(alpha_log[chA], beta_log[chA], a0, b0);
       snake_params<false>(alpha_log[chA + 1], beta_log[chA + 1], a1, b1);
-      act1d_window2<V>(wd, ow, pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
-#pragma unroll
-      for (int q = 0; q < V; ++q) outw[q * 4] = ow[q];
+      act1d_window2<V>([&](int j) { return unpack_bf16x2(wd[j]); },
+                       [&](int q, float ya, float yb) { outw[q * 4] = pack2(ya, yb); },
+                       pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
     } else if (any_valid) {
       uint32_t wd[V + 16];
 #pragma unroll

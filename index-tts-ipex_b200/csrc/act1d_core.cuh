@@ -122,11 +122,11 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f
 // bf16x2 word (lo = channel A, hi = channel B) -> (float A, float B)
 __device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
-// wd[j] = packed row tg-8+j of the two channels (j = 0..V+15); outw[q] = packed output row tg+q.
+// Two signals (channels) at once.  load(j) returns the pair of samples at window position j (= time tg-8+j),
+// j in [3, V+13); store(q, ya, yb) receives output tg+q of both signals.
 // sc0 = (2 e^alphaA, 2 e^alphaB), sc1 = (hbA, hbB), nsc1 = -sc1  (fast snake, see snake<false>).
-template <int V>
-__device__ __forceinline__ void act1d_window2(const uint32_t (&wd)[V + 16], uint32_t (&outw)[V], f32x2 sc0, f32x2 sc1,
-                                              f32x2 nsc1) {
+template <int V, class Load, class Store>
+__device__ __forceinline__ void act1d_window2(Load load, Store store, f32x2 sc0, f32x2 sc1, f32x2 nsc1) {
   const f32x2 g0 = pk2(2.f * BVG_F0, 2.f * BVG_F0), g1 = pk2(2.f * BVG_F1, 2.f * BVG_F1),
               g2 = pk2(2.f * BVG_F2, 2.f * BVG_F2), g3 = pk2(2.f * BVG_F3, 2.f * BVG_F3),
               g4 = pk2(2.f * BVG_F4, 2.f * BVG_F4), g5 = pk2(2.f * BVG_F5, 2.f * BVG_F5);
@@ -134,10 +134,10 @@ __device__ __forceinline__ void act1d_window2(const uint32_t (&wd)[V + 16], uint
   f32x2 X[V + 16];      // unpacked rows (only p+3..p+8 are live around intermediate pair p)
   f32x2 a[2 * V + 10];  // activated intermediates, a[i] <-> m = 2*tg - 5 + i (12 live at a time)
 #pragma unroll
-  for (int j = 3; j < 8; ++j) X[j] = unpack_bf16x2(wd[j]);
+  for (int j = 3; j < 8; ++j) X[j] = load(j);
 #pragma unroll
   for (int p = 0; p < V + 5; ++p) {
-    X[p + 8] = unpack_bf16x2(wd[p + 8]);
+    X[p + 8] = load(p + 8);
     // i = 2p (m odd):  g1 x[c-2] + g3 x[c-1] + g5 x[c] + g4 x[c+1] + g2 x[c+2] + g0 x[c+3], c = 5+p
     f32x2 u = mul2(g1, X[p + 3]);
     u = fma2(g3, X[p + 4], u);
@@ -169,8 +169,7 @@ __device__ __forceinline__ void act1d_window2(const uint32_t (&wd)[V + 16], uint
       s = fma2(g5, add2(a[i + 5], a[i + 6]), s);
       float yx, yy;
       unpk2(mul2(s, half), yx, yy);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(yx, yy);
-      outw[p - 5] = *reinterpret_cast<uint32_t*>(&h2);
+      store(p - 5, yx, yy);
     }
   }
 }
