@@ -410,6 +410,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
 #pragma unroll
               for (int j = 0; j < 8; ++j) if (co + j < P.Cout) f[j] += cond[co + j];
             }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (P.post_scale) {                                       // eval-BatchNorm folded to an affine (ECAPA TDNN)
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (co + j < P.Cout) f[j] = fmaf(f[j], P.post_scale[co + j], P.post_shift[co + j]);
+            }
+            if (P.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+            }
             if (r1) { float e[8]; unpack8(e1[g], e);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] += e[j]; }
@@ -595,6 +608,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
   P.dbg = ep.dbg;
   P.dry = ep.dry;
+  P.relu = ep.relu; P.post_scale = ep.post_scale; P.post_shift = ep.post_shift; P.act = ep.act;
   P.transposed = L.transposed;
   P.dil = L.dil;
   const int acc_cols = P.MT * P.NPH * P.NB;

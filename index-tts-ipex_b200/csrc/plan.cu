@@ -201,8 +201,8 @@ int make_bn(bvg_plan* P, const std::string& p, int Cn, float** scale, float** sh
 }
 
 int make_tdnn(bvg_plan* P, const std::string& p, int Cin, int Cout, int K, int dil, Tdnn* t, int ci_lo = 0,
-              int ci_hi = -1) {
-  BVG_TRY(make_conv(P, p + ".conv.conv.weight", p + ".conv.conv.bias", Cout, Cin, K, false, &t->conv, ci_lo, ci_hi));
+              int ci_hi = -1, int umma_nph = 0) {
+  BVG_TRY(make_conv(P, p + ".conv.conv.weight", p + ".conv.conv.bias", Cout, Cin, K, false, &t->conv, ci_lo, ci_hi, umma_nph));
   BVG_TRY(make_bn(P, p + ".norm.norm", Cout, &t->bn_scale, &t->bn_shift));
   t->dil = dil;
   return BVG_OK;
@@ -258,6 +258,7 @@ struct Bump {
 
 struct EcapaWs {
   float *X0, *Y1, *Y2, *Y3, *XL, *M, *A1, *A2, *sem, *se1, *se2, *ms, *actx, *pooled;
+  void *cx, *cy;           // c8t bf16 staging for the GEMM-shaped layers on the tensor-core path
 };
 void carve_ecapa(Bump& b, int64_t Bm, int64_t Tm, EcapaWs* w) {
   w->X0 = b.takef(Bm * kEC * Tm); w->Y1 = b.takef(Bm * kEC * Tm); w->Y2 = b.takef(Bm * kEC * Tm);
@@ -265,6 +266,7 @@ void carve_ecapa(Bump& b, int64_t Bm, int64_t Tm, EcapaWs* w) {
   w->A1 = b.takef(Bm * kEA * Tm); w->A2 = b.takef(Bm * kEM * Tm);
   w->sem = b.takef(Bm * kEC); w->se1 = b.takef(Bm * kEA); w->se2 = b.takef(Bm * kEC);
   w->ms = b.takef(Bm * 2 * kEM); w->actx = b.takef(Bm * kEA); w->pooled = b.takef(Bm * 2 * kEM);
+  w->cx = b.take(c8t_bytes(Bm, kEM, Tm)); w->cy = b.take(c8t_bytes(Bm, kEM, Tm));
 }
 
 // conv on [B,C,T]-contiguous fp32 tensors viewed through explicit strides
@@ -285,9 +287,25 @@ int tdnn_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64
   return conv_f32(dst, dsb, src, src2, sb, sc, st_, t.conv, ep, B, T, t.dil, 1, st);
 }
 
+// A 1x1 TDNN layer (a plain GEMM over B*T columns) on the tcgen05 path: fp32 [B,C,T] -> c8t bf16 -> conv_umma with
+// the bias / cond / ReLU / folded-BN / tanh epilogue -> fp32 [B,C,T].  Used by the bf16 decode path only.
+int tdnn_umma(float* dst, const float* src, int64_t sb, int64_t sc, int64_t st_, const ConvLayer& L,
+              const float* bn_scale, const float* bn_shift, int relu, int act, const float* cond, int64_t B, int64_t T,
+              const EcapaWs& w, cudaStream_t st) {
+  C8T x = make_c8t(w.cx, L.Cin, (int)T), y = make_c8t(w.cy, L.Cout, (int)T);
+  BVG_TRY(to_c8t_launch(x, src, sb, sc, st_, BVG_F32, B, st));
+  UmmaLayer u;
+  u.w = L.wu; u.Cin = L.Cin; u.Cout = L.Cout; u.K = 1; u.dil = 1;
+  UmmaEpilogue ep;
+  ep.bias = L.bias; ep.cond = cond; ep.cond_B = B; ep.relu = relu; ep.post_scale = bn_scale; ep.post_shift = bn_shift;
+  ep.act = act;
+  BVG_TRY(conv_umma_launch(u, x, y, ep, B, st));
+  return from_c8t_launch(dst, y, BVG_F32, B, st);
+}
+
 // ECAPA_TDNN.forward (ECAPA_TDNN.py:543-581), lengths=None.  mel [Bm,Tm,num_mels] -> spk [Bm,E]
 int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, float* spk, const EcapaWs& w,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool tc = false) {
   const int NM = P->cfg.num_mels;
   BVG_CHECK_ARG(Tm >= 5, "speaker encoder: reference mel needs >= 5 frames for reflect padding (got %lld)", (long long)Tm);
   // x.transpose(1,2): read channels-last mel through strides
@@ -296,7 +314,8 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
   int64_t Xsb = kEC * Tm;
   for (int i = 0; i < 3; ++i) {
     const SERes2& S = P->e_blk[i];
-    BVG_TRY(tdnn_f32(w.Y1, kEC * Tm, X, nullptr, Xsb, Tm, 1, S.tdnn1, Bm, Tm, st));
+    if (tc) BVG_TRY(tdnn_umma(w.Y1, X, Xsb, Tm, 1, S.tdnn1.conv, S.tdnn1.bn_scale, S.tdnn1.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+    else BVG_TRY(tdnn_f32(w.Y1, kEC * Tm, X, nullptr, Xsb, Tm, 1, S.tdnn1, Bm, Tm, st));
     // Res2NetBlock :179-191: 8 chunks of 64 channels, y_i = f(x_i + y_{i-1})
     const int CH = kEC / 8;
     BVG_CUDA(cudaMemcpy2DAsync(w.Y2, kEC * Tm * 4, w.Y1, kEC * Tm * 4, (size_t)CH * Tm * 4, Bm,
@@ -306,7 +325,8 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
       BVG_TRY(tdnn_f32(w.Y2 + (int64_t)j * CH * Tm, kEC * Tm, w.Y1 + (int64_t)j * CH * Tm, s2, kEC * Tm, Tm, 1,
                        S.r2n[j - 1], Bm, Tm, st));
     }
-    BVG_TRY(tdnn_f32(w.Y3, kEC * Tm, w.Y2, nullptr, kEC * Tm, Tm, 1, S.tdnn2, Bm, Tm, st));
+    if (tc) BVG_TRY(tdnn_umma(w.Y3, w.Y2, kEC * Tm, Tm, 1, S.tdnn2.conv, S.tdnn2.bn_scale, S.tdnn2.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+    else BVG_TRY(tdnn_f32(w.Y3, kEC * Tm, w.Y2, nullptr, kEC * Tm, Tm, 1, S.tdnn2, Bm, Tm, st));
     // SEBlock :228-242
     BVG_TRY(row_mean_launch(w.sem, w.Y3, Bm * kEC, Tm, st));
     ConvEpilogue e1; e1.relu = 1;
@@ -317,15 +337,22 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
     BVG_TRY(scale_residual_launch(out, kEM * Tm, w.se2, w.Y3, X, Xsb, Bm, kEC, Tm, st));
     X = out; Xsb = kEM * Tm;
   }
-  BVG_TRY(tdnn_f32(w.M, kEM * Tm, w.XL, nullptr, kEM * Tm, Tm, 1, P->e_mfa, Bm, Tm, st));
+  if (tc) BVG_TRY(tdnn_umma(w.M, w.XL, kEM * Tm, Tm, 1, P->e_mfa.conv, P->e_mfa.bn_scale, P->e_mfa.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+  else BVG_TRY(tdnn_f32(w.M, kEM * Tm, w.XL, nullptr, kEM * Tm, Tm, 1, P->e_mfa, Bm, Tm, st));
   // AttentiveStatisticsPooling :282-338.  The tdnn over cat([x, mean, std]) splits into a conv over x
   // plus a per-utterance term from (mean, std).
   BVG_TRY(row_stats_launch(w.ms, w.M, Bm, kEM, Tm, st));
   ConvEpilogue ec;
   BVG_TRY(conv_f32(w.actx, kEA, w.ms, nullptr, 2 * kEM, 1, 1, P->e_asp_ctx, ec, Bm, 1, 1, 0, st));
-  BVG_TRY(tdnn_f32(w.A1, kEA * Tm, w.M, nullptr, kEM * Tm, Tm, 1, P->e_asp_tdnn, Bm, Tm, st, w.actx, /*tanh*/ 1));
-  ConvEpilogue ea;
-  BVG_TRY(conv_f32(w.A2, kEM * Tm, w.A1, nullptr, kEA * Tm, Tm, 1, P->e_asp_conv, ea, Bm, Tm, 1, 0, st));
+  if (tc) {
+    BVG_TRY(tdnn_umma(w.A1, w.M, kEM * Tm, Tm, 1, P->e_asp_tdnn.conv, P->e_asp_tdnn.bn_scale, P->e_asp_tdnn.bn_shift, 1,
+                      /*tanh*/ 1, w.actx, Bm, Tm, w, st));
+    BVG_TRY(tdnn_umma(w.A2, w.A1, kEA * Tm, Tm, 1, P->e_asp_conv, nullptr, nullptr, 0, 0, nullptr, Bm, Tm, w, st));
+  } else {
+    BVG_TRY(tdnn_f32(w.A1, kEA * Tm, w.M, nullptr, kEM * Tm, Tm, 1, P->e_asp_tdnn, Bm, Tm, st, w.actx, /*tanh*/ 1));
+    ConvEpilogue ea;
+    BVG_TRY(conv_f32(w.A2, kEM * Tm, w.A1, nullptr, kEA * Tm, Tm, 1, P->e_asp_conv, ea, Bm, Tm, 1, 0, st));
+  }
   BVG_TRY(attn_stats_launch(w.pooled, w.A2, w.M, P->asp_bn_scale, P->asp_bn_shift, Bm, kEM, Tm, st));
   ConvEpilogue ef;
   BVG_TRY(conv_f32(spk, P->cfg.speaker_embedding_dim, w.pooled, nullptr, 2 * kEM, 1, 1, P->e_fc, ef, Bm, 1, 1, 0, st));
@@ -691,21 +718,21 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
   for (int i = 0; i < 3; ++i) {
     const std::string b = S + "blocks." + std::to_string(i + 1);
     SERes2& R = P->e_blk[i];
-    BVG_TRY(make_tdnn(P, b + ".tdnn1", kEC, kEC, 1, 1, &R.tdnn1));
+    BVG_TRY(make_tdnn(P, b + ".tdnn1", kEC, kEC, 1, 1, &R.tdnn1, 0, -1, um));
     for (int j = 0; j < 7; ++j)
       BVG_TRY(make_tdnn(P, b + ".res2net_block.blocks." + std::to_string(j), kEC / 8, kEC / 8, 3, i + 2, &R.r2n[j]));
-    BVG_TRY(make_tdnn(P, b + ".tdnn2", kEC, kEC, 1, 1, &R.tdnn2));
+    BVG_TRY(make_tdnn(P, b + ".tdnn2", kEC, kEC, 1, 1, &R.tdnn2, 0, -1, um));
     BVG_TRY(make_conv(P, b + ".se_block.conv1.conv.weight", b + ".se_block.conv1.conv.bias", kEA, kEC, 1, false, &R.se1));
     BVG_TRY(make_conv(P, b + ".se_block.conv2.conv.weight", b + ".se_block.conv2.conv.bias", kEC, kEA, 1, false, &R.se2));
   }
-  BVG_TRY(make_tdnn(P, S + "mfa", kEM, kEM, 1, 1, &P->e_mfa));
+  BVG_TRY(make_tdnn(P, S + "mfa", kEM, kEM, 1, 1, &P->e_mfa, 0, -1, um));
   // asp.tdnn over cat([x, mean, std]) (4608 ch): x part keeps ReLU+BN, the (mean,std) part becomes a
   // per-utterance additive term that also carries the conv bias
-  BVG_TRY(make_tdnn(P, S + "asp.tdnn", 3 * kEM, kEA, 1, 1, &P->e_asp_tdnn, 0, kEM));
+  BVG_TRY(make_tdnn(P, S + "asp.tdnn", 3 * kEM, kEA, 1, 1, &P->e_asp_tdnn, 0, kEM, um));
   BVG_TRY(make_conv(P, S + "asp.tdnn.conv.conv.weight", "", kEA, 3 * kEM, 1, false, &P->e_asp_ctx, kEM, 3 * kEM));
   P->e_asp_ctx.bias = P->e_asp_tdnn.conv.bias;
   P->e_asp_tdnn.conv.bias = nullptr;
-  BVG_TRY(make_conv(P, S + "asp.conv.conv.weight", S + "asp.conv.conv.bias", kEM, kEA, 1, false, &P->e_asp_conv));
+  BVG_TRY(make_conv(P, S + "asp.conv.conv.weight", S + "asp.conv.conv.bias", kEM, kEA, 1, false, &P->e_asp_conv, 0, -1, um));
   BVG_TRY(make_bn(P, S + "asp_bn.norm", 2 * kEM, &P->asp_bn_scale, &P->asp_bn_shift));
   BVG_TRY(make_conv(P, S + "fc.conv.weight", S + "fc.conv.bias", E, 2 * kEM, 1, false, &P->e_fc));
   BVG_CUDA(cudaDeviceSynchronize());
@@ -758,7 +785,7 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
   const int E = c.speaker_embedding_dim;
   const float* spk = spk_in;
   if (mel) {
-    BVG_TRY(ecapa_forward(P, mel, Bm, Tm, g.spk, g.e, st));
+    BVG_TRY(ecapa_forward(P, mel, Bm, Tm, g.spk, g.e, st, /*tensor cores*/ dtype == BVG_BF16 && P->umma));
     spk = g.spk;
   }
   // speaker conditioning vectors cond_layer(spk), conds[i](spk)  (models.py:226, :233-234): [Bm, C]

@@ -38,6 +38,10 @@ struct UmmaEpilogue {
   const __nv_bfloat16* res1 = nullptr;  // same c8t geometry as the output
   const __nv_bfloat16* res2 = nullptr;
   float scale = 1.f;
+  int relu = 0;                       // ReLU after bias/cond (ECAPA TDNN: conv -> ReLU -> BN)
+  const float* post_scale = nullptr;  // [Cout] folded eval-BN affine applied after the ReLU
+  const float* post_shift = nullptr;
+  int act = 0;                        // 1: tanh after the affine
   int zero_pads = 0;                  // also (re)write the output's zero halo rows
   int dry = 0;                        // debug: run only the MMA issue loop (no TMA, waits or epilogue)
   long long* dbg = nullptr;           // optional [grid][8] cycle counters (profiling builds of the tests)
@@ -60,6 +64,8 @@ struct UmmaConvParams {
   int dry;
   int n_issuers;
   int transposed, dil;
+  int relu, act;
+  const float* post_scale; const float* post_shift;
 };
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
