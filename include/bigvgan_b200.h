@@ -113,6 +113,12 @@ BVG_API int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log
  * (148 CTAs max) into this device buffer: producer wait, MMA waits on input / weights / TMEM, MMA issue,
  * MMA-thread total, epilogue wait, epilogue busy. */
 BVG_API void bvg_debug_set_umma_counters(long long* dev_buf);
+/* Activation1d(src) -> Conv1d (+bias, +res1, *scale) in ONE kernel (narrow layers, Cout <= 128): the form the
+ * bf16 decode path uses for AMPBlock1's act->conv pairs (models.py:65-74).  Plain [B,C,T] bf16 in/out; status 3
+ * when the shape does not qualify.  Test entry point (allocates temporaries). */
+BVG_API int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                         const float* weight, const float* bias, const void* res1, float scale,
+                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);
 BVG_API int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
                         const void* res1, const void* res2, float scale,
                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);

@@ -402,6 +402,9 @@ int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, in
                             L.Cout, T, L.K, dil, 0, dtype, dtype, st);
 }
 
+// BVG_NO_FUSE=1 keeps Activation1d and the convs in separate kernels everywhere (A/B testing of the fusion)
+const bool g_fuse_act = [] { const char* e = getenv("BVG_NO_FUSE"); return !(e && e[0] == '1'); }();
+
 UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1) {
   UmmaLayer u;
   u.w = L.wu; u.bias = L.bias; u.Cin = L.Cin; u.Cout = L.Cout; u.K = L.K; u.dil = dil;
@@ -442,23 +445,35 @@ int decode_bf16_umma(const bvg_plan* P, const float* latent, const GenWs& g, int
       const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
       const C8T* cur = &a;
       for (int m = 0; m < 3; ++m) {
-        BVG_TRY(act1d_c8t_launch(t1, *cur, R.alpha[2 * m], R.beta[2 * m], B, st));
+        // xt = c1(a1(x)): one fused kernel for narrow layers, Activation1d kernel + conv kernel otherwise
         UmmaEpilogue e1;
         e1.bias = R.c1[m].bias;
-        BVG_TRY(conv_umma_launch(ulayer(R.c1[m], R.dil[m]), t1, t2, e1, B, st));
-        BVG_TRY(act1d_c8t_launch(t1, t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, st));
+        int rc = g_fuse_act ? conv_umma_fused_launch(ulayer(R.c1[m], R.dil[m]), *cur, R.alpha[2 * m], R.beta[2 * m], t2, e1, B, st)
+                            : BVG_ERR_STATE;
+        if (rc == BVG_ERR_STATE) {
+          BVG_TRY(act1d_c8t_launch(t1, *cur, R.alpha[2 * m], R.beta[2 * m], B, st));
+          rc = conv_umma_launch(ulayer(R.c1[m], R.dil[m]), t1, t2, e1, B, st);
+        }
+        BVG_TRY(rc);
+        // x = c2(a2(xt)) + x   (and the 3-block sum / mean on the last pair)
         UmmaEpilogue e2;
         e2.bias = R.c2[m].bias;
         e2.res1 = cur->p;
-        if (m < 2) {
-          BVG_TRY(conv_umma_launch(ulayer(R.c2[m], 1), t1, y, e2, B, st));
-          cur = &y;
-        } else {
+        const C8T* out = &y;
+        if (m == 2) {
           if (j > 0) e2.res2 = xs.p;
           if (j == c.num_kernels - 1) e2.scale = inv_nk;
           e2.zero_pads = 1;
-          BVG_TRY(conv_umma_launch(ulayer(R.c2[m], 1), t1, xs, e2, B, st));
+          out = &xs;
         }
+        rc = g_fuse_act ? conv_umma_fused_launch(ulayer(R.c2[m], 1), t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], *out, e2, B, st)
+                        : BVG_ERR_STATE;
+        if (rc == BVG_ERR_STATE) {
+          BVG_TRY(act1d_c8t_launch(t1, t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, st));
+          rc = conv_umma_launch(ulayer(R.c2[m], 1), t1, *out, e2, B, st);
+        }
+        BVG_TRY(rc);
+        if (m < 2) cur = &y;
       }
     }
   }
@@ -553,6 +568,7 @@ int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, const floa
   return rc;
 }
 
+
 static long long* g_umma_dbg = nullptr;   // set by bvg_debug_set_umma_counters (profiling only)
 static int g_umma_dry = 0;
 void bvg_debug_set_umma_counters(long long* dev_buf) {
@@ -610,6 +626,40 @@ int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const 
   if (rc == BVG_OK) rc = to_c8t_launch(x, src, Cn * T, T, 1, BVG_BF16, B, st);
   if (rc == BVG_OK && cudaMemsetAsync(x.p, 0x7f, (size_t)x.pad * 16, st) != cudaSuccess) rc = BVG_ERR_CUDA;
   if (rc == BVG_OK) rc = act1d_c8t_launch(y, x, alpha_log, beta_log, B, st);
+  if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
+int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                         const float* weight, const float* bias, const void* res1, float scale, int64_t B, int64_t Cin,
+                         int64_t Cout, int64_t T, int K, int dilation, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(dst && src && weight && alpha_log && beta_log && B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1, "actconv: bad argument");
+  const size_t xb = c8t_bytes(B, (int)Cin, T), yb = c8t_bytes(B, (int)Cout, T);
+  const size_t wb = (size_t)umma_pack_elems((int)Cout, (int)Cin, K, 1) * 2;
+  char* tmp = nullptr;
+  BVG_CUDA(cudaMallocAsync((void**)&tmp, xb + 2 * yb + wb + 1024, st));
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  C8T x = make_c8t(tmp, (int)Cin, (int)T);
+  C8T y = make_c8t(tmp + al(xb), (int)Cout, (int)T);
+  C8T r1 = make_c8t(tmp + al(xb) + al(yb), (int)Cout, (int)T);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(tmp + al(xb) + 2 * al(yb));
+  int rc = BVG_OK;
+  if (cudaMemsetAsync(tmp, 0x7f, xb, st) != cudaSuccess) rc = BVG_ERR_CUDA;      // poison: halo rows must not matter
+  if (rc == BVG_OK) rc = to_c8t_launch(x, src, Cin * T, T, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK && cudaMemsetAsync(x.p, 0x7f, (size_t)x.pad * 16, st) != cudaSuccess) rc = BVG_ERR_CUDA;
+  if (rc == BVG_OK && res1) rc = to_c8t_launch(r1, res1, Cout * T, T, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK) rc = umma_pack_launch(wp, weight, (int)Cout, (int)Cin, K, 0, 1, st);
+  if (rc == BVG_OK) {
+    UmmaLayer L;
+    L.w = wp; L.Cin = (int)Cin; L.Cout = (int)Cout; L.K = K; L.dil = dilation;
+    UmmaEpilogue ep;
+    ep.bias = bias; ep.scale = scale; ep.res1 = res1 ? r1.p : nullptr;
+    ep.dbg = g_umma_dbg;
+    rc = conv_umma_fused_launch(L, x, alpha_log, beta_log, y, ep, B, st);
+    if (rc == BVG_ERR_STATE) set_error("actconv: this layer shape does not qualify for the fused kernel");
+  }
   if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
   cudaFreeAsync(tmp, st);
   return rc;

@@ -65,6 +65,8 @@ struct UmmaConvParams {
   int n_issuers;
   int transposed, dil;
   int relu, act;
+  int Cin;                            // true input channels (fused activation)
+  const float* act_alpha; const float* act_beta;   // fused Activation1d parameters (log scale), or null
   const float* post_scale; const float* post_shift;
 };
 
@@ -73,6 +75,9 @@ int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
                      int nph, cudaStream_t st);
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
+// Activation1d -> Conv1d in one kernel for narrow layers; BVG_ERR_STATE (nothing launched) if the layer does not qualify
+int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,
+                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
 // Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)

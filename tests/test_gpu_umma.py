@@ -89,3 +89,31 @@ def test_act1d_c8t_vs_oracle(P, Cn, T):
     # and it agrees with the plain-layout kernel to the last bit of the bf16 output
     y2 = P.anti_alias_activation_forward(xd, None, None, ad, bd)
     assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("Cin,Cout,T,K,dil", [(96, 96, 1000, 3, 1), (96, 96, 700, 11, 5), (96, 96, 260, 7, 3), (48, 48, 2049, 11, 5),
+                                               (48, 48, 513, 3, 1), (24, 24, 4100, 7, 1), (24, 24, 300, 11, 3), (24, 24, 5, 3, 1),
+                                               (96, 96, 13, 3, 1), (64, 128, 257, 3, 1)])
+def test_fused_actconv_equals_unfused(P, Cin, Cout, T, K, dil):
+    """The fused Activation1d->conv kernel must reproduce the two-kernel path bit for bit (same stencil,
+    same MMA order), including at the sequence edges and across tile boundaries."""
+    gen = torch.Generator().manual_seed(Cin * 3 + T + K)
+    B = 2
+    x = _bf(torch.randn(B, Cin, T, generator=gen) * 1.5).cuda()
+    a = (torch.randn(Cin, generator=gen) * 0.5).cuda()
+    b = (torch.randn(Cin, generator=gen) * 0.5).cuda()
+    w = _bf(torch.randn(Cout, Cin, K, generator=gen) / (Cin * K) ** 0.5).float().cuda()
+    bias = torch.randn(Cout, generator=gen).cuda()
+    r1 = _bf(torch.randn(B, Cout, T, generator=gen)).cuda()
+    L = P.capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    act = torch.empty_like(x)
+    P.capi.check(L.bvg_act1d_c8t_fwd(act.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), B, Cin, T, st))
+    y_ref = torch.empty(B, Cout, T, device="cuda", dtype=torch.bfloat16)
+    P.capi.check(L.bvg_conv1d_umma_fwd(y_ref.data_ptr(), act.data_ptr(), w.data_ptr(), bias.data_ptr(), r1.data_ptr(), None,
+                                       0.5, B, Cin, Cout, T, K, dil, st))
+    y = torch.empty_like(y_ref)
+    P.capi.check(L.bvg_actconv_umma_fwd(y.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                        r1.data_ptr(), 0.5, B, Cin, Cout, T, K, dil, st), "bvg_actconv_umma_fwd")
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref), float((y.float() - y_ref.float()).abs().max())
