@@ -80,12 +80,19 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
     for (int c = 0; c < nch; ++c)
       bulk_g2s(in + c * RIN + (lo - (r0 - 8)), x + (base + (int64_t)(ch0 + c) * Tp + lo) * 8, bytes, bar);
   }
-  mbar_wait(bar, 0);
-
   const int lane = tid & 31, warp = tid >> 5;
   const int pp = lane & 3;
   const int cg = (lane >> 2) % NCH;
   const int rg = warp * RGW + (lane >> 2) / NCH;                  // 16-row group within the tile
+  // snake parameters first: their global-load latency overlaps the TMA wait
+  float pa0 = 0.f, pb0 = 0.f, pa1 = 0.f, pb1 = 0.f;
+  {
+    const int chP = (ch0 + cg) * 8 + 2 * pp;
+    if (cg < nch && chP < C) snake_params<false>(alpha_log[chP], beta_log[chP], pa0, pb0);
+    if (cg < nch && chP + 1 < C) snake_params<false>(alpha_log[chP + 1], beta_log[chP + 1], pa1, pb1);
+  }
+  mbar_wait(bar, 0);
+
   if (cg < nch) {
     const int64_t t0 = (int64_t)r0 + V * rg - pad;                // time index of this thread's first output
     const uint32_t* inw = reinterpret_cast<const uint32_t*>(in) + (size_t)(cg * RIN + V * rg) * 4 + pp;
@@ -98,9 +105,7 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
       uint32_t wd[V + 16];
 #pragma unroll
       for (int j = 3; j < V + 13; ++j) wd[j] = inw[j * 4];
-      float a0, b0, a1, b1;
-      snake_params<false>(alpha_log[chA], beta_log[chA], a0, b0);
-      snake_params<false>(alpha_log[chA + 1], beta_log[chA + 1], a1, b1);
+      const float a0 = pa0, b0 = pb0, a1 = pa1, b1 = pb1;
       act1d_window2<V>([&](int j) { return unpack_bf16x2(wd[j]); },
                        [&](int q, float ya, float yb) { outw[q * 4] = pack2(ya, yb); },
                        pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
@@ -118,9 +123,7 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
 #pragma unroll
           for (int j = 0; j < V + 16; ++j)
             xw[j] = h ? __uint_as_float(wd[j] & 0xffff0000u) : __uint_as_float(wd[j] << 16);
-          float sc0, sc1;
-          snake_params<false>(alpha_log[ch], beta_log[ch], sc0, sc1);
-          act1d_window<V, false>(xw, yv, sc0, sc1, t0, (int64_t)T);
+          act1d_window<V, false>(xw, yv, h ? pa1 : pa0, h ? pb1 : pb0, t0, (int64_t)T);
 #pragma unroll
           for (int q = 0; q < V; ++q)
             if (t0 + q < 0 || t0 + q >= T) yv[q] = 0.f;           // zero halo rows

@@ -533,15 +533,15 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  else if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");   // 4*40 + 4*72 + 12*120 = 1888 <= 20 warps * 96 (the CTA pool)
-
+  // Register re-balancing (setmaxnreg is per warpgroup; each role's code sits inside the branch that sets its budget):
+  // 4*48 + 4*72 + 12*120 = 1920 = the 20 warps x 96 registers the CTA was launched with.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == 0) {
-    // ===================== TMA producer: raw input rows + weights =====================
+    // ===================== TMA producer 1: raw input rows =====================
     if (lane == 0) {
-      int rs = 0, ws = 0;
-      uint32_t rph = 0, wph = 0;
+      int rs = 0;
+      uint32_t rph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile % P.tiles_per_batch;
         const int b = tile / P.tiles_per_batch;
@@ -559,27 +559,31 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             bulk_g2s(smem_u32(rsm + rs * raw_stage_bytes) + (kc * XRAW + (lo_r - r0)) * 16,
                      xb + ((int64_t)(cb * 8 + kc) * P.x_tp + lo_r) * 8, nbytes, &full_raw[rs]);
           if (++rs == kFStages) { rs = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer 2: weights (own warp: a full weight ring must not delay the raw rows) =====
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (P.w_resident && tile != (int)blockIdx.x) break;          // resident weights are fetched once
+        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
+          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
           const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
           const __nv_bfloat16* wsrc = P.w + (int64_t)cb * 64 * P.NB * P.ntaps;
-          if (P.w_resident) {
-            if (tile == (int)blockIdx.x)
-              for (int tp = 0; tp < P.ntaps; ++tp) {
-                const int slot = cb * P.ntaps + tp;
-                mbar_expect_tx(&full_w[slot], wbytes);
-                bulk_g2s(smem_u32(wsm + slot * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[slot]);
-              }
-          } else {
-            for (int tp = 0; tp < P.ntaps; ++tp) {
-              mbar_wait(&empty_w[ws], wph ^ 1);
-              mbar_expect_tx(&full_w[ws], wbytes);
-              bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
-              if (++ws == kWStages) { ws = 0; wph ^= 1; }
-            }
+          for (int tp = 0; tp < P.ntaps; ++tp) {
+            const int slot = P.w_resident ? cb * P.ntaps + tp : ws;
+            if (!P.w_resident) mbar_wait(&empty_w[ws], wph ^ 1);
+            mbar_expect_tx(&full_w[slot], wbytes);
+            bulk_g2s(smem_u32(wsm + slot * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[slot]);
+            if (!P.w_resident && ++ws == kWStages) { ws = 0; wph ^= 1; }
           }
         }
       }
     }
-  } else if (warp < 4) {
+  } else {
     // ===================== MMA issuers (as in conv_umma_kernel, conv taps only) =====================
     const int ii = warp - 1;
     if (ii < n_iss) {
@@ -635,7 +639,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       }
       if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 8; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; }
     }
+  }
   } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
@@ -650,6 +656,19 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
       const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
+      if (r1 || r2) {
+        // the residual rows this thread will add do not depend on the MMAs: pull them towards the SM now
+        for (int a = 0; a < nacc; ++a) {
+          const int64_t t = (int64_t)q0 + a * 128 + r;
+          if (t >= P.Tout) continue;
+          const int64_t rowoff = ((int64_t)P.y_row0 + t) * 8;
+          for (int ch = 0; ch < P.y_chunks; ++ch) {
+            const int64_t off = (int64_t)ch * P.y_tp * 8 + rowoff;
+            if (r1) asm volatile("prefetch.global.L1 [%0];" ::"l"(r1 + off));
+            if (r2) asm volatile("prefetch.global.L1 [%0];" ::"l"(r2 + off));
+          }
+        }
+      }
       { DBG_T0(); mbar_wait(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       DBG_T0();
@@ -712,6 +731,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
     }
     if (P.dbg && threadIdx.x == 128) { P.dbg[blockIdx.x * 8 + 6] = dbg_ewait; P.dbg[blockIdx.x * 8 + 7] = dbg_ebusy; }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     // ===================== activation warps: raw tile -> Activation1d -> A-operand tile =====================
     constexpr int V = 16;
     const int aw = warp - 8;                                        // 0..7
@@ -730,17 +750,18 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         const int nch = kcn > 4 ? 8 : 4;
         const int cg = (lane >> 2) % nch;
         const int sub = (lane >> 2) / nch;                          // 0, or 0..1 when nch == 4
-        const int slots = kFActWarps * (8 / nch);
+        const int per_warp = 8 / nch;                               // row groups a warp takes per claim
+        const int chA = (cb * 8 + cg) * 8 + 2 * pp;
+        // snake parameters first: their global-load latency hides behind the barrier waits below
+        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+        if (cg < kcn && chA < P.Cin) snake_params<false>(P.act_alpha[chA], P.act_beta[chA], a0, b0);
+        if (cg < kcn && chA + 1 < P.Cin) snake_params<false>(P.act_alpha[chA + 1], P.act_beta[chA + 1], a1, b1);
         { DBG_T0(); mbar_wait(&full_raw[rs], rph); DBG_ADD(dbg_araw); }
         { DBG_T0(); mbar_wait(&empty_x[xs], xph ^ 1); DBG_ADD(dbg_ax); }
         DBG_T0();
         const uint32_t* raw = reinterpret_cast<const uint32_t*>(rsm + rs * raw_stage_bytes);
         uint32_t* xo = reinterpret_cast<uint32_t*>(xsm + xs * x_stage_bytes);
-        const int chA = (cb * 8 + cg) * 8 + 2 * pp;
-        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-        if (cg < kcn && chA < P.Cin) snake_params<false>(P.act_alpha[chA], P.act_beta[chA], a0, b0);
-        if (cg < kcn && chA + 1 < P.Cin) snake_params<false>(P.act_alpha[chA + 1], P.act_beta[chA + 1], a1, b1);
-        for (int rg = aw * (8 / nch) + sub; rg < ngroups; rg += slots) {
+        for (int rg = aw * per_warp + sub; rg < ngroups; rg += kFActWarps * per_warp) {
           if (cg >= kcn) continue;
           const int j0 = rg * V;                                    // first A-tile row of this group
           const int64_t t0 = t_first + j0;
@@ -1050,7 +1071,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   P.B = (int)B;
   P.n_issuers = 2;
   P.kc_max = std::min(8, P.Cin_p / 8);
-  const size_t fixed = (size_t)(4 * kFStages + 2 * kMaxWStages + 4) * 8 + 16 + (size_t)P.NB * 4 + 128;
+  const size_t fixed = (size_t)(4 * kFStages + 2 * kMaxWStages + 4) * 8 + 32 + (size_t)P.NB * 4 + 128;
   const size_t budget = 227 * 1024 - fixed;
   const size_t rsb = (size_t)(P.XR + 16) * P.kc_max * 16, xsb = (size_t)P.XR * P.kc_max * 16, wsb = (size_t)P.NB * P.kc_max * 16;
   const size_t stage_bytes = kFStages * (rsb + xsb);
