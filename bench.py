@@ -29,6 +29,15 @@ UP = 1024
 AUDIO_S_PER_UTT = T0 * UP / SR
 
 
+def workload_config(batch, precision, world):
+    """The `config` object both arms print (same workload; the reference arm runs a bounded sample of it)."""
+    return {"workload": f"IndexTTS-1.5 BigVGAN decode (random init), {batch} x 10 s utterances per GPU "
+                        f"(T0={T0} latent frames, Tm={TM} mel frames), {precision} storage, utterance-sharded; "
+                        f"N>1 adds one NCCL all_gather of the fp32 waveforms per step",
+            "global_batch": world * batch, "audio_s_per_step": world * batch * AUDIO_S_PER_UTT,
+            "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,8 +163,9 @@ def run_reference(args):
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"IndexTTS-1.5 BigVGAN decode, {B_PER_GPU} x 10 s utterances per GPU "
-                               f"(T0={T0}, Tm={TM}); reference arm runs a bounded sample on the host CPU"},
+        "config": workload_config(args.batch, args.precision, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
+        "reference_note": "the reference's algorithm (oracle port, torch fp32) on the host CPU; each step is a bounded "
+                          "sample of the workload",
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -265,8 +275,11 @@ def run_ours(args):
             roof = {"kernel": "act1d_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": act_gbs / pk["hbm"], "traffic": None}
         else:
-            roof = {"kernel": "conv1d (all dense generator convs)", "bound": "tensor", "achieved": conv_tf,
-                    "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": conv_tf / pk["tf_sustained"], "traffic": None}
+            roof = {"kernel": "conv_umma_kernel (all dense generator convs of the step)", "bound": "tensor",
+                    "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": conv_tf / pk["tf_sustained"], "traffic": None,
+                    "traffic_note": "per-launch DRAM bytes of representative launches are in profiles/r01_ncu_full_summary.txt "
+                                    "(C=96 k=3: 688 MB measured vs 740 MB algorithmic)"}
         roof["peak_source"] = pk["src"] + (" sustained" if roof["bound"] == "tensor" else " copy")
         roof["launches_per_step"] = per_step[dom][1]
         roof["avg_launch_ms"] = per_step[dom][0] / max(per_step[dom][1], 1)
@@ -277,11 +290,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"IndexTTS-1.5 BigVGAN decode (random init), {B} x 10 s utterances per GPU "
-                                   f"(T0={T0} latent frames, Tm={TM} mel frames), {args.precision} storage, "
-                                   f"utterance-sharded; N>1 adds one NCCL all_gather of the fp32 waveforms per step",
-                       "global_batch": world * B, "audio_s_per_step": world * B * AUDIO_S_PER_UTT,
-                       "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush"},
+            "config": workload_config(B, args.precision, world),
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "api": "BigVGAN.decode_host -> bvg_decode_host (pinned host buffers)"},
             "gpu_launches": int(nl.item()),

@@ -215,6 +215,160 @@ int launch_typed(void* dst, const void* src, const float* a, const float* b, int
   return BVG_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast-math variant on packed fp32x2 (FFMA2): a thread owns TWO rows (channels) x 16 consecutive samples, so
+// every FIR multiply-add pairs up across the two rows and the issue-slot count per sample halves (see
+// act1d_core.cuh::act1d_window2).  One CTA = 16 rows x 512 samples (+8-sample halo per side), staged by TMA
+// bulk copies like the kernel above.  Used when precise == 0; the libdevice-sinf parity path keeps the scalar kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPRows = 16;
+constexpr int kPW = 512;
+constexpr int kPPitch = kPW + 2 * kHalo;       // 528 elements
+
+template <typename T> __device__ __forceinline__ float ld_f(const T* p, int i) { return to_f<T>(p[i]); }
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(256, 2)
+act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __restrict__ alpha_log,
+                  const float* __restrict__ beta_log, int64_t rows, int C, int64_t Tlen, int col_tiles) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  T (*tile)[kPPitch] = reinterpret_cast<T (*)[kPPitch]>(smem_raw);
+  T (*otile)[kPW] = reinterpret_cast<T (*)[kPW]>(smem_raw + sizeof(T) * kPRows * kPPitch);     // results, row-major
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(T) * kPRows * (kPPitch + kPW));
+
+  const int tid = threadIdx.x;
+  const int64_t blk = blockIdx.x;
+  const int64_t row0 = (blk / col_tiles) * kPRows;
+  const int64_t t0 = (blk % col_tiles) * (int64_t)kPW;
+  const int nrows = (int)min((int64_t)kPRows, rows - row0);
+
+  // thread = row pair (tid >> 5) x 16-sample group (tid & 31)
+  const int r = (tid >> 5) * 2;
+  const int c0 = (tid & 31) * 16;
+  const int64_t tg = t0 + c0;
+  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;     // snake parameters first: the loads overlap the TMA wait
+  if (r < nrows) snake_params<false>(alpha_log[(int)((row0 + r) % C)], beta_log[(int)((row0 + r) % C)], a0, b0);
+  if (r + 1 < nrows) snake_params<false>(alpha_log[(int)((row0 + r + 1) % C)], beta_log[(int)((row0 + r + 1) % C)], a1, b1);
+
+  if (ALIGNED) {
+    const int64_t lo = max(t0 - kHalo, (int64_t)0);
+    const int64_t hi = min(t0 + kPW + kHalo, Tlen);
+    const uint32_t bytes = (uint32_t)((hi - lo) * sizeof(T));
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, bytes * nrows);
+      for (int rr = 0; rr < nrows; ++rr)
+        bulk_g2s(&tile[rr][lo - (t0 - kHalo)], src + (row0 + rr) * Tlen + lo, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    for (int idx = tid; idx < kPRows * kPPitch; idx += 256) {
+      const int rr = idx / kPPitch, c = idx % kPPitch;
+      const int64_t t = t0 - kHalo + c;
+      T v = from_f<T>(0.f);
+      if (rr < nrows && t >= 0 && t < Tlen) v = src[(row0 + rr) * Tlen + t];
+      tile[rr][c] = v;
+    }
+    __syncthreads();
+  }
+  constexpr int V = 16;
+  if (r < nrows && tg < Tlen) {
+  const int nr = min(2, nrows - r);
+  const bool interior = (tg - 5 >= 0) && (tg + V + 4 <= Tlen - 1) && nr == 2;
+  if (interior) {
+    // window position j <-> tile[row][c0 + j] (time tg - 8 + j); rows are fetched 16 bytes at a time as the stencil
+    // walks down the window (everything is unrolled, so `j` is a compile-time constant in each call)
+    constexpr int VE = 16 / sizeof(T);                     // elements per 128-bit shared-memory load
+    const uint4* va = reinterpret_cast<const uint4*>(&tile[r][c0]);
+    const uint4* vb = reinterpret_cast<const uint4*>(&tile[r + 1][c0]);
+    uint4 ca = va[0], cb = vb[0];
+    float ya[V], yb[V];
+    act1d_window2<V>(
+        [&](int j) {
+          if (j % VE == 0) { ca = va[j / VE]; cb = vb[j / VE]; }
+          const int e = j % VE;
+          float fa, fb;
+          if (sizeof(T) == 4) {
+            const uint32_t wa = e == 0 ? ca.x : e == 1 ? ca.y : e == 2 ? ca.z : ca.w;
+            const uint32_t wb = e == 0 ? cb.x : e == 1 ? cb.y : e == 2 ? cb.z : cb.w;
+            fa = __uint_as_float(wa); fb = __uint_as_float(wb);
+          } else {
+            const int w = e >> 1;
+            const uint32_t wa = w == 0 ? ca.x : w == 1 ? ca.y : w == 2 ? ca.z : ca.w;
+            const uint32_t wb = w == 0 ? cb.x : w == 1 ? cb.y : w == 2 ? cb.z : cb.w;
+            const uint16_t ha = (e & 1) ? (uint16_t)(wa >> 16) : (uint16_t)(wa & 0xffffu);
+            const uint16_t hb = (e & 1) ? (uint16_t)(wb >> 16) : (uint16_t)(wb & 0xffffu);
+            fa = to_f<T>(*reinterpret_cast<const T*>(&ha)); fb = to_f<T>(*reinterpret_cast<const T*>(&hb));
+          }
+          return pk2(fa, fb);
+        },
+        [&](int q, float va_, float vb_) { ya[q] = va_; yb[q] = vb_; },
+        pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
+    store8_vec<T>(&otile[r][c0], *reinterpret_cast<float(*)[8]>(&ya[0]));
+    store8_vec<T>(&otile[r][c0 + 8], *reinterpret_cast<float(*)[8]>(&ya[8]));
+    store8_vec<T>(&otile[r + 1][c0], *reinterpret_cast<float(*)[8]>(&yb[0]));
+    store8_vec<T>(&otile[r + 1][c0 + 8], *reinterpret_cast<float(*)[8]>(&yb[8]));
+  } else {
+    for (int h = 0; h < nr; ++h) {          // sequence edges / odd last row: scalar stencil with replicate padding
+      float xw[V + 16], y[V];
+#pragma unroll
+      for (int j = 0; j < V + 16; ++j) xw[j] = to_f<T>(tile[r + h][c0 + j]);
+      act1d_window<V, false>(xw, y, h ? a1 : a0, h ? b1 : b0, tg, Tlen);
+#pragma unroll
+      for (int q = 0; q < V; ++q) otile[r + h][c0 + q] = from_f<T>(y[q]);
+    }
+  }
+  }
+  // results leave row by row: TMA bulk stores when rows are 16-byte aligned, coalesced stores otherwise
+  const int ncols = (int)min((int64_t)kPW, Tlen - t0);
+  if (ALIGNED) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid < nrows) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (row0 + tid) * Tlen + t0),
+                   "r"(smem_u32(&otile[tid][0])), "r"((uint32_t)(ncols * sizeof(T))) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (int idx = tid; idx < nrows * kPW; idx += 256) {
+      const int rr = idx / kPW, c = idx % kPW;
+      if (c < ncols) dst[(row0 + rr) * Tlen + t0 + c] = otile[rr][c];
+    }
+  }
+}
+
+template <typename T>
+int launch_pair(void* dst, const void* src, const float* a, const float* b, int64_t rows, int64_t C, int64_t Tlen,
+                cudaStream_t st) {
+  const int64_t col_tiles = (Tlen + kPW - 1) / kPW;
+  const int64_t row_groups = (rows + kPRows - 1) / kPRows;
+  const int64_t nblk = col_tiles * row_groups;
+  BVG_CHECK_ARG(nblk < (1ll << 31), "act1d: problem too large (%lld CTAs)", (long long)nblk);
+  const bool aligned = (Tlen % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  const size_t smem = sizeof(T) * kPRows * (kPPitch + kPW) + 16;
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  ProfScope prof(st, KC_ACT1D);
+  T* d = static_cast<T*>(dst);
+  const T* s = static_cast<const T*>(src);
+  if (aligned) act1d_pair_kernel<T, true><<<(unsigned)nblk, 256, smem, st>>>(d, s, a, b, rows, (int)C, Tlen, (int)col_tiles);
+  else act1d_pair_kernel<T, false><<<(unsigned)nblk, 256, smem, st>>>(d, s, a, b, rows, (int)C, Tlen, (int)col_tiles);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
 }  // namespace
 
 int act1d_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log,
@@ -224,6 +378,14 @@ int act1d_launch(void* dst, const void* src, const float* alpha_log, const float
   BVG_CHECK_ARG(B >= 0 && C > 0 && T >= 0 && C < (1ll << 31), "act1d: bad shape B=%lld C=%lld T=%lld", (long long)B, (long long)C, (long long)T);
   if (B == 0 || T == 0) return BVG_OK;
   const int64_t rows = B * C;
+  if (!precise) {
+    switch (dtype) {
+      case BVG_F32: return launch_pair<float>(dst, src, alpha_log, beta_log, rows, C, T, st);
+      case BVG_BF16: return launch_pair<__nv_bfloat16>(dst, src, alpha_log, beta_log, rows, C, T, st);
+      case BVG_F16: return launch_pair<__half>(dst, src, alpha_log, beta_log, rows, C, T, st);
+      default: set_error("act1d: unsupported dtype %d", dtype); return BVG_ERR_INVALID;
+    }
+  }
   switch (dtype) {
     case BVG_F32: return launch_typed<float>(dst, src, alpha_log, beta_log, rows, C, T, precise, st);
     case BVG_BF16: return launch_typed<__nv_bfloat16>(dst, src, alpha_log, beta_log, rows, C, T, precise, st);

@@ -95,6 +95,7 @@ struct ConvEpilogue {
   const float* post_scale = nullptr;  // [Cout] eval-BN folded affine applied after ReLU
   const float* post_shift = nullptr;
   int act = 0;                      // 0 none, 1 tanh, 2 sigmoid (applied last)
+  int prof_other = 0;               // account this launch to the "other" profiling class (speaker encoder)
 };
 
 // src element (b, ci, t) lives at src[b*sb + ci*sc + t*st_] (src2, when non-null, has the same

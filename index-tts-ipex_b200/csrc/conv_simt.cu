@@ -272,7 +272,7 @@ int conv1d_simt_launch(void* dst, int64_t dsb, const void* src, const void* src2
   BVG_CHECK_ARG(B <= 65535 && (Cout + kTC - 1) / kTC <= 65535, "conv1d: batch/channel grid too large");
   dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)((Cout + kTC - 1) / kTC), (unsigned)B);
   EpiDev e = to_dev(ep);
-  ProfScope prof(st, T >= 64 ? KC_CONV : KC_OTHER);
+  ProfScope prof(st, (T >= 64 && !ep.prof_other) ? KC_CONV : KC_OTHER);
   if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
     conv1d_simt_kernel<float, float><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
                                                            sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);

@@ -56,6 +56,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
+// same wait for warps that are off the critical path (producer, epilogue): back off between polls so the spin
+// does not take issue slots from the MMA-issuing warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
         const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;    // first staged row within a chunk
         for (int cb = 0; cb < P.n_ci_blk; ++cb) {
           const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-          { DBG_T0(); mbar_wait(&empty_x[xs], xph ^ 1); DBG_ADD(dbg_prod_wait); }
+          { DBG_T0(); mbar_wait_relaxed(&empty_x[xs], xph ^ 1); DBG_ADD(dbg_prod_wait); }
           mbar_expect_tx(&full_x[xs], (uint32_t)kcn * P.XR * 16u);
           for (int kc = 0; kc < kcn; ++kc)
             bulk_g2s(smem_u32(xsm + xs * x_stage_bytes) + kc * P.XR * 16,
@@ -243,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
               }
           } else {
             for (int tp = 0; tp < P.ntaps; ++tp) {
-              { DBG_T0(); mbar_wait(&empty_w[ws], wph ^ 1); DBG_ADD(dbg_prod_wait); }
+              { DBG_T0(); mbar_wait_relaxed(&empty_w[ws], wph ^ 1); DBG_ADD(dbg_prod_wait); }
               mbar_expect_tx(&full_w[ws], wbytes);
               bulk_g2s(smem_u32(wsm + ws * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[ws]);
               if (++ws == kWStages) { ws = 0; wph ^= 1; }
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
       const float* cond = P.cond ? P.cond + (int64_t)(P.cond_B == 1 ? 0 : b) * P.Cout : nullptr;
       const float* bs = bias_s + nb * P.NB;
-      { DBG_T0(); mbar_wait(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
+      { DBG_T0(); mbar_wait_relaxed(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       DBG_T0();
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
@@ -1019,7 +1031,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
     BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
-  ProfScope prof(st, L.transposed ? KC_CONVTR : KC_CONV);
+  ProfScope prof(st, ep.prof_other ? KC_OTHER : (L.transposed ? KC_CONVTR : KC_CONV));
   conv_umma_kernel<<<grid, kThreads, smem, st>>>(P);
   BVG_LAUNCHED();
   return BVG_OK;

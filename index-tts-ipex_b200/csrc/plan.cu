@@ -283,7 +283,7 @@ int tdnn_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64
              const Tdnn& t, int64_t B, int64_t T, cudaStream_t st, const float* cond = nullptr, int act = 0) {
   ConvEpilogue ep;
   ep.relu = 1; ep.post_scale = t.bn_scale; ep.post_shift = t.bn_shift; ep.act = act;
-  ep.cond = cond; ep.cond_B = B;
+  ep.cond = cond; ep.cond_B = B; ep.prof_other = 1;
   return conv_f32(dst, dsb, src, src2, sb, sc, st_, t.conv, ep, B, T, t.dil, 1, st);
 }
 
@@ -298,7 +298,7 @@ int tdnn_umma(float* dst, const float* src, int64_t sb, int64_t sc, int64_t st_,
   u.w = L.wu; u.Cin = L.Cin; u.Cout = L.Cout; u.K = 1; u.dil = 1;
   UmmaEpilogue ep;
   ep.bias = L.bias; ep.cond = cond; ep.cond_B = B; ep.relu = relu; ep.post_scale = bn_scale; ep.post_shift = bn_shift;
-  ep.act = act;
+  ep.act = act; ep.prof_other = 1;
   BVG_TRY(conv_umma_launch(u, x, y, ep, B, st));
   return from_c8t_launch(dst, y, BVG_F32, B, st);
 }

@@ -42,6 +42,7 @@ struct UmmaEpilogue {
   const float* post_scale = nullptr;  // [Cout] folded eval-BN affine applied after the ReLU
   const float* post_shift = nullptr;
   int act = 0;                        // 1: tanh after the affine
+  int prof_other = 0;                 // account this launch to the "other" profiling class (speaker encoder)
   int zero_pads = 0;                  // also (re)write the output's zero halo rows
   int dry = 0;                        // debug: run only the MMA issue loop (no TMA, waits or epilogue)
   long long* dbg = nullptr;           // optional [grid][8] cycle counters (profiling builds of the tests)
