@@ -303,3 +303,21 @@ def test_error_behaviour(P):
         m(latent.cuda(), mel.cuda()[:, :3])                    # too few mel frames for reflect padding
     with pytest.raises(NotImplementedError):
         m(latent.cuda(), mel.cuda(), lens=torch.ones(2))
+
+
+def test_cuda_graph_decode_matches_eager(P):
+    """The whole decode is capturable (no allocation, no sync inside the library call)."""
+    m, sd, h = _model(P, "small", 5, "wild")
+    latent, mel = O.synthetic_inputs(h, 2, 11, 30, seed=21)
+    for prec in ("fp32", "bf16"):
+        m.precision = prec
+        try:
+            eager = m.decode(latent.cuda(), mel_ref=mel.cuda())
+            run = m.make_graphed_decode(2, 11, 30)
+            a = run(latent.cuda(), mel.cuda()).clone()
+            latent2, mel2 = O.synthetic_inputs(h, 2, 11, 30, seed=22)
+            b = run(latent2.cuda(), mel2.cuda()).clone()
+            eager2 = m.decode(latent2.cuda(), mel_ref=mel2.cuda())
+        finally:
+            m.precision = None
+        assert torch.equal(a, eager) and torch.equal(b, eager2)

@@ -24,3 +24,17 @@ for prec in ("fp32", "bf16"):
     ts.sort()
     P.capi.profile_begin(); m.decode(lat, mel_ref=mel); prof = P.capi.profile_end()
     print(f"{prec}: B=1 x 10.03 s  median {ts[len(ts)//2]:.2f} ms  min {ts[0]:.2f} ms  -> {10.027/ (ts[len(ts)//2]/1e3):.0f} x real time; classes {prof}")
+
+for prec in ("fp32", "bf16"):
+    m.precision = prec
+    run = m.make_graphed_decode(1, 235, 281)
+    for _ in range(3):
+        run(lat, mel)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(lat, mel); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"{prec} CUDA graph: median {ts[len(ts)//2]:.2f} ms  min {ts[0]:.2f} ms")
