@@ -308,7 +308,7 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
           return pk2(fa, fb);
         },
         [&](int q, float va_, float vb_) { ya[q] = va_; yb[q] = vb_; },
-        pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
+        pk2(a0, a1), pk2(b0, b1));
     store8_vec<T>(&otile[r][c0], *reinterpret_cast<float(*)[8]>(&ya[0]));
     store8_vec<T>(&otile[r][c0 + 8], *reinterpret_cast<float(*)[8]>(&ya[8]));
     store8_vec<T>(&otile[r + 1][c0], *reinterpret_cast<float(*)[8]>(&yb[0]));

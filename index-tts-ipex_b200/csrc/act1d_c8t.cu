@@ -108,7 +108,7 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
       const float a0 = pa0, b0 = pb0, a1 = pa1, b1 = pb1;
       act1d_window2<V>([&](int j) { return unpack_bf16x2(wd[j]); },
                        [&](int q, float ya, float yb) { outw[q * 4] = pack2(ya, yb); },
-                       pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
+                       pk2(a0, a1), pk2(b0, b1));
     } else if (any_valid) {
       uint32_t wd[V + 16];
 #pragma unroll

@@ -124,15 +124,19 @@ __device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) { return pk2(__uint_a
 
 // Two signals (channels) at once.  load(j) returns the pair of samples at window position j (= time tg-8+j),
 // j in [3, V+13); store(q, ya, yb) receives output tg+q of both signals.
-// sc0 = (2 e^alphaA, 2 e^alphaB), sc1 = (hbA, hbB), nsc1 = -sc1  (fast snake, see snake<false>).
+// sc0 = (2 e^alphaA, 2 e^alphaB), sc1 = (hbA, hbB)  (fast snake, see snake<false>).
+// The intermediates are kept at half scale (a' = a/2, an exact power-of-two scaling folded into the snake's
+// constants), so the down-FIR can reuse the doubled taps g = 2f of the up-FIR without a final multiply:
+// sum g a' == sum f a, rounding for rounding.
 template <int V, class Load, class Store>
-__device__ __forceinline__ void act1d_window2(Load load, Store store, f32x2 sc0, f32x2 sc1, f32x2 nsc1) {
+__device__ __forceinline__ void act1d_window2(Load load, Store store, f32x2 sc0, f32x2 sc1) {
   const f32x2 g0 = pk2(2.f * BVG_F0, 2.f * BVG_F0), g1 = pk2(2.f * BVG_F1, 2.f * BVG_F1),
               g2 = pk2(2.f * BVG_F2, 2.f * BVG_F2), g3 = pk2(2.f * BVG_F3, 2.f * BVG_F3),
               g4 = pk2(2.f * BVG_F4, 2.f * BVG_F4), g5 = pk2(2.f * BVG_F5, 2.f * BVG_F5);
   const f32x2 half = pk2(0.5f, 0.5f);
+  const f32x2 sc1h = mul2(sc1, half), nsc1h = mul2(sc1, pk2(-0.5f, -0.5f));
   f32x2 X[V + 16];      // unpacked rows (only p+3..p+8 are live around intermediate pair p)
-  f32x2 a[2 * V + 10];  // activated intermediates, a[i] <-> m = 2*tg - 5 + i (12 live at a time)
+  f32x2 a[2 * V + 10];  // activated intermediates (half scale), a[i] <-> m = 2*tg - 5 + i (12 live at a time)
 #pragma unroll
   for (int j = 3; j < 8; ++j) X[j] = load(j);
 #pragma unroll
@@ -155,9 +159,9 @@ __device__ __forceinline__ void act1d_window2(Load load, Store store, f32x2 sc0,
     {
       float zx, zy;
       unpk2(mul2(u, sc0), zx, zy);
-      a[2 * p] = fma2(nsc1, pk2(__cosf(zx), __cosf(zy)), add2(u, sc1));
+      a[2 * p] = fma2(nsc1h, pk2(__cosf(zx), __cosf(zy)), fma2(u, half, sc1h));
       unpk2(mul2(w, sc0), zx, zy);
-      a[2 * p + 1] = fma2(nsc1, pk2(__cosf(zx), __cosf(zy)), add2(w, sc1));
+      a[2 * p + 1] = fma2(nsc1h, pk2(__cosf(zx), __cosf(zy)), fma2(w, half, sc1h));
     }
     if (p >= 5) {
       const int i = 2 * (p - 5);
@@ -168,7 +172,7 @@ __device__ __forceinline__ void act1d_window2(Load load, Store store, f32x2 sc0,
       s = fma2(g4, add2(a[i + 4], a[i + 7]), s);
       s = fma2(g5, add2(a[i + 5], a[i + 6]), s);
       float yx, yy;
-      unpk2(mul2(s, half), yx, yy);
+      unpk2(s, yx, yy);
       store(p - 5, yx, yy);
     }
   }

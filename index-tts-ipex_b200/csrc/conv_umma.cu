@@ -29,6 +29,7 @@
 #include "act1d_core.cuh"
 #include "bvg_common.cuh"
 #include "umma.cuh"
+#include "umma_ptx.cuh"
 
 namespace bvg {
 namespace {
@@ -40,141 +41,6 @@ constexpr int kMaxIssuers = 4;                         // MMA-issuing warps (one
 constexpr int kEpiWarp0 = 1 + kMaxIssuers;             // first epilogue warp (kEpiWarp0 % 4 == 1)
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-// same wait for warps that are off the critical path (producer, epilogue): back off between polls so the spin
-// does not take issue slots from the MMA-issuing warps that share the scheduler
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  for (;;) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (done) break;
-    __nanosleep(64);
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;   // descriptor version (Blackwell)
-  return d;          // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE (0)
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// one elected lane of a fully converged warp (CUTLASS elect_one_sync): keeps the surrounding control flow
-// warp-uniform, so descriptors live in uniform registers and tcgen05.mma needs no per-lane serialisation
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-// D[tmem] (+)= A * B with the descriptors given as (lo, shared hi) words; executed by one elected lane of a
-// converged warp, all operands warp-uniform
-__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p, e;\n.reg .b64 da, db;\n"
-      "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-// single-thread form: descriptor hi word (SBO = 128 B, version 1, no swizzle) is an immediate, so only the two
-// lo words and the accumulator address change between MMAs
-__device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
-      "mov.b64 da, {%1, 0x4008};\nmov.b64 db, {%2, 0x4008};\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
-  asm volatile(
-      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// NK back-to-back MMAs along K (one per 16 input channels), fully unrolled so that every MMA gets its own
-// uniform registers for the two descriptors and the issue does not serialise on them
-template <int NK>
-__device__ __forceinline__ void issue_k(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum,
-                                        uint32_t astep, uint32_t bstep) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    umma_bf16(d, ad + (uint64_t)(k * astep), bd + (uint64_t)(k * bstep), idesc, k ? 1u : accum);
-  }
-}
-
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    f[2 * j] = __uint_as_float(w[j] << 16);
-    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-  }
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// optional per-role cycle accounting (UmmaConvParams::dbg != nullptr): 8 counters per CTA
-#define DBG_T0() const long long dbg_t0__ = P.dbg ? clock64() : 0
-#define DBG_ADD(var) do { if (P.dbg) (var) += clock64() - dbg_t0__; } while (0)
 
 // Persistent kernel: each CTA walks tiles (m_tile, n_block, batch) with a static stride; the smem rings and
 // the TMEM accumulator stages keep flowing across tiles, so the epilogue of tile i overlaps the
@@ -478,371 +344,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   }
 }
 
-// =====================================================================================================
-// Fused Activation1d -> Conv1d (narrow layers, one output-channel block).
-//
-// AMPBlock1 always feeds its convs with an Activation1d output (models.py:65-74: xt = c1(a1(x)); xt = c2(a2(xt))).
-// For C <= 96 both ops are HBM-bound, so here the activated tensor never exists in HBM: the TMA producer stages
-// the RAW input tile (conv rows + 8-row FIR halo), eight "activation" warps run the packed-fp32x2 stencil of
-// act1d_core.cuh on it and write the result straight into the K-major UMMA A-operand tile in shared memory
-// (zero rows where the conv pads), and the MMA issuers / epilogue proceed exactly as in conv_umma_kernel.
-// HBM traffic per layer pair drops from 9 tensor passes to 5, and the FIR math overlaps the MMAs and stores.
-//
-// Warp roles (640 threads): warp 0 TMA producer, warps 1-2 MMA issuers, warps 4-7 epilogue (one per TMEM lane
-// quarter), warps 8-19 activation.  The FIR stencil is the bottleneck and wants 128 registers x as many warps as
-// possible, so the register file is re-balanced with setmaxnreg: control warpgroup 40, epilogue 72, activation 120 (the sum must not exceed the 20 x 96 the CTA was launched with).
-constexpr int kFThreads = 640;    // 5 warpgroups: control (producer + issuers), epilogue, 3 x activation
-constexpr int kFActWarps = 12;
-constexpr int kFStages = 2;       // raw-input stages and A-operand stages
-
-__global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const UmmaConvParams P) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  const int kWStages = P.w_stages;
-  const int XRAW = P.XR + 16;
-  const uint32_t raw_stage_bytes = (uint32_t)XRAW * P.kc_max * 16u;
-  const uint32_t x_stage_bytes = (uint32_t)P.XR * P.kc_max * 16u;
-  const uint32_t w_stage_bytes = (uint32_t)P.NB * P.kc_max * 16u;
-  uint8_t* rsm = smem;
-  uint8_t* xsm = rsm + kFStages * raw_stage_bytes;
-  uint8_t* wsm = xsm + kFStages * x_stage_bytes;
-  uint8_t* tail = wsm + kWStages * w_stage_bytes;
-  uint64_t* full_raw = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_raw = full_raw + kFStages;
-  uint64_t* full_x = empty_raw + kFStages;
-  uint64_t* empty_x = full_x + kFStages;
-  uint64_t* full_w = empty_x + kFStages;
-  uint64_t* empty_w = full_w + kMaxWStages;
-  uint64_t* tmem_full = empty_w + kMaxWStages;                    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                           // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [NB]
-
-  const int nacc = P.MT;                                           // conv only: one accumulator per time sub-tile
-  const int acc_cols = nacc * P.NB;
-  const int ntiles = P.tiles_per_batch * P.B;
-  const int n_iss = P.n_issuers;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kFStages; ++i) {
-      mbar_init(&full_raw[i], 1); mbar_init(&empty_raw[i], kFActWarps);
-      mbar_init(&full_x[i], kFActWarps); mbar_init(&empty_x[i], n_iss);
-    }
-    for (int i = 0; i < kWStages; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], n_iss); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], n_iss); mbar_init(&tmem_empty[i], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(P.tmem_cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (warp >= 4 && warp < 8)
-    for (int i = threadIdx.x - 128; i < P.NB; i += 128) bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // Register re-balancing (setmaxnreg is per warpgroup; each role's code sits inside the branch that sets its budget):
-  // 4*48 + 4*72 + 12*120 = 1920 = the 20 warps x 96 registers the CTA was launched with.
-  if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-  if (warp == 0) {
-    // ===================== TMA producer 1: raw input rows =====================
-    if (lane == 0) {
-      int rs = 0;
-      uint32_t rph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mt = tile % P.tiles_per_batch;
-        const int b = tile / P.tiles_per_batch;
-        const int q0 = mt * P.MT * 128;
-        const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
-        // raw tile row i <-> padded-space row r0 + i, r0 = x_row0 + q0 - lo - 8; clipped to the chunk [0, x_tp)
-        const int r0 = P.x_row0 + q0 - P.lo - 8;
-        const int lo_r = max(r0, 0), hi_r = min(r0 + XRAW, P.x_tp);
-        const uint32_t nbytes = (uint32_t)(hi_r - lo_r) * 16u;
-        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-          mbar_wait(&empty_raw[rs], rph ^ 1);
-          mbar_expect_tx(&full_raw[rs], nbytes * kcn);
-          for (int kc = 0; kc < kcn; ++kc)
-            bulk_g2s(smem_u32(rsm + rs * raw_stage_bytes) + (kc * XRAW + (lo_r - r0)) * 16,
-                     xb + ((int64_t)(cb * 8 + kc) * P.x_tp + lo_r) * 8, nbytes, &full_raw[rs]);
-          if (++rs == kFStages) { rs = 0; rph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== TMA producer 2: weights (own warp: a full weight ring must not delay the raw rows) =====
-    if (lane == 0) {
-      int ws = 0;
-      uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (P.w_resident && tile != (int)blockIdx.x) break;          // resident weights are fetched once
-        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-          const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-          const uint32_t wbytes = (uint32_t)P.NB * kcn * 16u;
-          const __nv_bfloat16* wsrc = P.w + (int64_t)cb * 64 * P.NB * P.ntaps;
-          for (int tp = 0; tp < P.ntaps; ++tp) {
-            const int slot = P.w_resident ? cb * P.ntaps + tp : ws;
-            if (!P.w_resident) mbar_wait(&empty_w[ws], wph ^ 1);
-            mbar_expect_tx(&full_w[slot], wbytes);
-            bulk_g2s(smem_u32(wsm + slot * w_stage_bytes), wsrc + (int64_t)tp * kcn * 8 * P.NB, wbytes, &full_w[slot]);
-            if (!P.w_resident && ++ws == kWStages) { ws = 0; wph ^= 1; }
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== MMA issuers (as in conv_umma_kernel, conv taps only) =====================
-    const int ii = warp - 1;
-    if (ii < n_iss) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)P.XR << 16, b_lbo = (uint32_t)P.NB << 16;
-      const uint32_t astep = 2u * P.XR, bstep = 2u * P.NB;
-      const uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
-      const uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
-      const int first_tile = blockIdx.x;
-      int xs = 0, ws = 0, as = 0;
-      uint32_t xph = 0, wph = 0, aph = 0;
-      long long dbg_wx = 0, dbg_wt = 0;
-      const long long dbg_start = P.dbg ? clock64() : 0;
-      for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
-        { DBG_T0(); mbar_wait(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dbase = tmem_base + (uint32_t)(as * acc_cols);
-        for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-          const int nk = min(8, (P.Cin_p - cb * 64) >> 3) >> 1;
-          { DBG_T0(); mbar_wait(&full_x[xs], xph); DBG_ADD(dbg_wx); }   // activation warps filled this A stage
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
-          for (int tp = 0; tp < P.ntaps; ++tp) {
-            const int slot = P.w_resident ? cb * P.ntaps + tp : ws;
-            if (!P.w_resident || tile == first_tile) {
-              mbar_wait(&full_w[slot], P.w_resident ? 0u : wph);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
-            const uint32_t accum0 = (cb > 0 || tp > 0) ? 1u : 0u;
-            if (lane == 0) {
-              const uint32_t a_tp = a_cb + (uint32_t)(tp * P.dil);
-              for (int ms = ii; ms < P.MT; ms += n_iss) {
-                const uint32_t d = dbase + (uint32_t)(ms * P.NB);
-                uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
-                umma_bf16_imm(d, am, bm, idesc, accum0);
-                for (int k = 1; k < nk; ++k) {
-                  am += astep; bm += bstep;
-                  umma_bf16_imm(d, am, bm, idesc, 1u);
-                }
-              }
-            }
-            if (!P.w_resident) {
-              umma_commit_elect(&empty_w[ws]);
-              if (++ws == kWStages) { ws = 0; wph ^= 1; }
-            }
-          }
-          umma_commit_elect(&empty_x[xs]);
-          if (++xs == kFStages) { xs = 0; xph ^= 1; }
-        }
-        umma_commit_elect(&tmem_full[as]);
-        if (++as == P.acc_stages) { as = 0; aph ^= 1; }
-      }
-      if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 8; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; }
-    }
-  }
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
-    const int wq = warp & 3;
-    const int r = wq * 32 + lane;
-    int as = 0;
-    uint32_t aph = 0;
-    const int ngrp16 = P.NB >> 4;
-    long long dbg_ewait = 0, dbg_ebusy = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int mt = tile % P.tiles_per_batch;
-      const int b = tile / P.tiles_per_batch;
-      const int q0 = mt * P.MT * 128;
-      __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
-      const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
-      const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
-      if (r1 || r2) {
-        // the residual rows this thread will add do not depend on the MMAs: pull them towards the SM now
-        for (int a = 0; a < nacc; ++a) {
-          const int64_t t = (int64_t)q0 + a * 128 + r;
-          if (t >= P.Tout) continue;
-          const int64_t rowoff = ((int64_t)P.y_row0 + t) * 8;
-          for (int ch = 0; ch < P.y_chunks; ++ch) {
-            const int64_t off = (int64_t)ch * P.y_tp * 8 + rowoff;
-            if (r1) asm volatile("prefetch.global.L1 [%0];" ::"l"(r1 + off));
-            if (r2) asm volatile("prefetch.global.L1 [%0];" ::"l"(r2 + off));
-          }
-        }
-      }
-      { DBG_T0(); mbar_wait(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      DBG_T0();
-      const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
-      for (int item = 0; item < nacc * ngrp16; ++item) {
-        const int a = item / ngrp16, c0 = (item - a * ngrp16) << 4;  // 16 accumulator columns per step (register diet)
-        const int64_t t = (int64_t)q0 + a * 128 + r;
-        const bool valid = t < P.Tout;
-        const int64_t rowoff = ((int64_t)P.y_row0 + (valid ? t : 0)) * 8;
-        uint4 e1[2], e2[2];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          e1[g] = make_uint4(0, 0, 0, 0); e2[g] = make_uint4(0, 0, 0, 0);
-          const int co = c0 + 8 * g;
-          if (valid && co < P.y_chunks * 8) {
-            const int64_t off = (int64_t)(co >> 3) * P.y_tp * 8 + rowoff;
-            if (r1) e1[g] = *reinterpret_cast<const uint4*>(r1 + off);
-            if (r2) e2[g] = *reinterpret_cast<const uint4*>(r2 + off);
-          }
-        }
-        uint32_t v[16];
-        tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!valid) continue;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int co = c0 + 8 * g;
-          if (co >= P.y_chunks * 8) continue;
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[co + j];
-          if (r1) { float e[8]; unpack8(e1[g], e);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
-          if (r2) { float e[8]; unpack8(e2[g], e);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += e[j]; }
-          uint4 o;
-          o.x = pack2(f[0] * P.scale, f[1] * P.scale); o.y = pack2(f[2] * P.scale, f[3] * P.scale);
-          o.z = pack2(f[4] * P.scale, f[5] * P.scale); o.w = pack2(f[6] * P.scale, f[7] * P.scale);
-          *reinterpret_cast<uint4*>(yb + (int64_t)(co >> 3) * P.y_tp * 8 + rowoff) = o;
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      DBG_ADD(dbg_ebusy);
-      if (++as == P.acc_stages) { as = 0; aph ^= 1; }
-      if (P.zero_pads) {
-        const int et = threadIdx.x - 128;
-        const int chn = P.y_chunks;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        if (mt == 0)
-          for (int i = et; i < chn * P.y_row0; i += 128)
-            *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
-        if (mt == P.tiles_per_batch - 1)
-          for (int i = et; i < chn * P.y_row0; i += 128)
-            *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
-      }
-    }
-    if (P.dbg && threadIdx.x == 128) { P.dbg[blockIdx.x * 8 + 6] = dbg_ewait; P.dbg[blockIdx.x * 8 + 7] = dbg_ebusy; }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    // ===================== activation warps: raw tile -> Activation1d -> A-operand tile =====================
-    constexpr int V = 16;
-    const int aw = warp - 8;                                        // 0..7
-    const int pp = lane & 3;                                        // 32-bit word (channel pair) within the 16-byte row
-    int rs = 0, xs = 0;
-    uint32_t rph = 0, xph = 0;
-    long long dbg_araw = 0, dbg_ax = 0, dbg_abusy = 0;
-    const int ngroups = (P.XR + V - 1) / V;                         // 16-row groups of the A tile
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int mt = tile % P.tiles_per_batch;
-      const int q0 = mt * P.MT * 128;
-      const int64_t t_first = (int64_t)q0 - P.lo;                   // time index of A-tile row 0
-      for (int cb = 0; cb < P.n_ci_blk; ++cb) {
-        const int kcn = min(8, (P.Cin_p - cb * 64) >> 3);
-        // lanes cover (word, chunk) x row-group slots: 8 chunks x 1 slot, or 4 chunks x 2 slots per warp
-        const int nch = kcn > 4 ? 8 : 4;
-        const int cg = (lane >> 2) % nch;
-        const int sub = (lane >> 2) / nch;                          // 0, or 0..1 when nch == 4
-        const int per_warp = 8 / nch;                               // row groups a warp takes per claim
-        const int chA = (cb * 8 + cg) * 8 + 2 * pp;
-        // snake parameters first: their global-load latency hides behind the barrier waits below
-        float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-        if (cg < kcn && chA < P.Cin) snake_params<false>(P.act_alpha[chA], P.act_beta[chA], a0, b0);
-        if (cg < kcn && chA + 1 < P.Cin) snake_params<false>(P.act_alpha[chA + 1], P.act_beta[chA + 1], a1, b1);
-        { DBG_T0(); mbar_wait(&full_raw[rs], rph); DBG_ADD(dbg_araw); }
-        { DBG_T0(); mbar_wait(&empty_x[xs], xph ^ 1); DBG_ADD(dbg_ax); }
-        DBG_T0();
-        const uint32_t* raw = reinterpret_cast<const uint32_t*>(rsm + rs * raw_stage_bytes);
-        uint32_t* xo = reinterpret_cast<uint32_t*>(xsm + xs * x_stage_bytes);
-        for (int rg = aw * per_warp + sub; rg < ngroups; rg += kFActWarps * per_warp) {
-          if (cg >= kcn) continue;
-          const int j0 = rg * V;                                    // first A-tile row of this group
-          const int64_t t0 = t_first + j0;
-          const uint32_t* inw = raw + (size_t)(cg * XRAW + j0) * 4 + pp;      // window row i <-> raw row j0 + i
-          uint32_t* outw = xo + (size_t)(cg * P.XR + j0) * 4 + pp;
-          const int nrow = min(V, P.XR - j0);
-          const bool interior = (t0 - 5 >= 0) && (t0 + V + 4 <= (int64_t)P.Tout - 1) && (chA + 1 < P.Cin) && nrow == V;
-          if (interior) {
-            uint32_t wd[V + 16];
-#pragma unroll
-            for (int j = 3; j < V + 13; ++j) wd[j] = inw[j * 4];
-            act1d_window2<V>([&](int j) { return unpack_bf16x2(wd[j]); },
-                             [&](int q, float ya, float yb) { outw[q * 4] = pack2(ya, yb); },
-                             pk2(a0, a1), pk2(b0, b1), pk2(-b0, -b1));
-          } else if ((t0 + V - 1 >= 0) && (t0 < P.Tout) && (chA < P.Cin)) {
-            uint32_t wd[V + 16];
-#pragma unroll
-            for (int j = 0; j < V + 16; ++j) wd[j] = (j0 + j < XRAW) ? inw[j * 4] : 0u;
-            float ylo[V];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float yv[V];
-              if (chA + h < P.Cin) {
-                float xw[V + 16];
-#pragma unroll
-                for (int j = 0; j < V + 16; ++j)
-                  xw[j] = h ? __uint_as_float(wd[j] & 0xffff0000u) : __uint_as_float(wd[j] << 16);
-                act1d_window<V, false>(xw, yv, h ? a1 : a0, h ? b1 : b0, t0, (int64_t)P.Tout);
-#pragma unroll
-                for (int q = 0; q < V; ++q)
-                  if (t0 + q < 0 || t0 + q >= P.Tout) yv[q] = 0.f;       // the conv's zero padding
-              } else {
-#pragma unroll
-                for (int q = 0; q < V; ++q) yv[q] = 0.f;
-              }
-              if (h == 0) {
-#pragma unroll
-                for (int q = 0; q < V; ++q) ylo[q] = yv[q];
-              } else {
-#pragma unroll
-                for (int q = 0; q < V; ++q)
-                  if (q < nrow) outw[q * 4] = pack2(ylo[q], yv[q]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < V; ++q)
-              if (q < nrow) outw[q * 4] = 0u;
-          }
-        }
-        // generic-proxy writes of the A tile -> visible to the tensor core's async-proxy reads
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&full_x[xs]); mbar_arrive(&empty_raw[rs]); }
-        DBG_ADD(dbg_abusy);
-        if (++rs == kFStages) { rs = 0; rph ^= 1; }
-        if (++xs == kFStages) { xs = 0; xph ^= 1; }
-      }
-    }
-    if (P.dbg && threadIdx.x == 256) { long long* d = P.dbg + blockIdx.x * 8; d[0] = dbg_araw; d[1] = dbg_ax; d[2] = dbg_abusy; }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols));
-  }
-}
-
 // torch-layout fp32 weight -> packed bf16 tiles [n_blk][ci_blk][tap][kchunk][NB][8], zero padded.
 // conv: src [Cout][Cin][K]; transposed: src [Cin][Cout][K].
 __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin,
@@ -1037,84 +538,6 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   return BVG_OK;
 }
 
-
-// Activation1d(x) -> Conv1d fused (see conv_umma_fused_kernel).  Returns BVG_ERR_STATE without launching when the
-// layer does not qualify (caller falls back to act1d_c8t_launch + conv_umma_launch).
-int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,
-                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st) {
-  if (L.transposed || !act_alpha || !act_beta) return BVG_ERR_STATE;
-  BVG_CHECK_ARG(L.w && x.p && y.p, "conv_umma_fused: null pointer");
-  BVG_CHECK_ARG(x.C == L.Cin && y.C == L.Cout && y.T == x.T, "conv_umma_fused: shape mismatch");
-  UmmaConvParams P;
-  memset(&P, 0, sizeof P);
-  int n_nblk = 1;
-  P.NPH = 1;
-  umma_choose_nb(L.Cout, 1, &P.NB, &n_nblk);
-  if (n_nblk != 1 || P.NB > 128 || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
-  P.ntaps = L.K;
-  BVG_CHECK_ARG(L.K <= 16, "conv_umma_fused: at most 16 taps");
-  P.MT = 2;
-  const int pad = L.dil * (L.K - 1) / 2;
-  // (raw rows below the chunk start are clipped by the producer; they only feed replicate-padded positions)
-  P.lo = pad;
-  P.dil = L.dil;
-  P.u = 1; P.p = 0;
-  P.Tout = y.T;
-  P.tiles_per_batch = (y.T + 255) / 256;
-  P.XR = 256 + L.dil * (L.K - 1);
-  P.Cin = L.Cin;
-  P.Cin_p = (L.Cin + 15) / 16 * 16;
-  BVG_CHECK_ARG(x.chunks * 8 >= P.Cin_p, "conv_umma_fused: input tensor must carry channel padding to a multiple of 16");
-  P.n_ci_blk = (P.Cin_p + 63) / 64;
-  P.Cout = L.Cout;
-  P.x = x.p; P.x_bstride = (int64_t)x.chunks * x.Tp * 8; P.x_tp = x.Tp; P.x_row0 = x.pad;
-  P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad; P.y_chunks = y.chunks;
-  P.w = L.w;
-  P.bias = ep.bias; P.scale = ep.scale; P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
-  P.act_alpha = act_alpha; P.act_beta = act_beta;
-  P.dbg = ep.dbg;
-  const int acc_cols = P.MT * P.NB;
-  P.acc_stages = 2;
-  int pw = 32;
-  while (pw < 2 * acc_cols) pw <<= 1;
-  if (pw > 512) return BVG_ERR_STATE;
-  P.tmem_cols = pw;
-  P.n_nblk = 1;
-  P.B = (int)B;
-  P.n_issuers = 2;
-  P.kc_max = std::min(8, P.Cin_p / 8);
-  const size_t fixed = (size_t)(4 * kFStages + 2 * kMaxWStages + 4) * 8 + 32 + (size_t)P.NB * 4 + 128;
-  const size_t budget = 227 * 1024 - fixed;
-  const size_t rsb = (size_t)(P.XR + 16) * P.kc_max * 16, xsb = (size_t)P.XR * P.kc_max * 16, wsb = (size_t)P.NB * P.kc_max * 16;
-  const size_t stage_bytes = kFStages * (rsb + xsb);
-  const int wslots = P.ntaps * P.n_ci_blk;
-  if (stage_bytes + 2 * wsb > budget) return BVG_ERR_STATE;
-  if (wslots <= kMaxWStages && stage_bytes + wslots * wsb <= budget) {
-    P.w_resident = 1;
-    P.w_stages = wslots;
-  } else {
-    P.w_resident = 0;
-    P.w_stages = (int)std::min<size_t>(kMaxWStages, (budget - stage_bytes) / wsb);
-  }
-  const size_t smem = stage_bytes + (size_t)P.w_stages * wsb + fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int64_t ntiles = (int64_t)P.tiles_per_batch * B;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    BVG_CUDA(cudaGetDevice(&dev));
-    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
-  ProfScope prof(st, KC_CONV);
-  conv_umma_fused_kernel<<<grid, kFThreads, smem, st>>>(P);
-  BVG_LAUNCHED();
-  return BVG_OK;
-}
 
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B,
                   cudaStream_t st) {

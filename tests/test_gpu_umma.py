@@ -93,7 +93,9 @@ def test_act1d_c8t_vs_oracle(P, Cn, T):
 
 @pytest.mark.parametrize("Cin,Cout,T,K,dil", [(96, 96, 1000, 3, 1), (96, 96, 700, 11, 5), (96, 96, 260, 7, 3), (48, 48, 2049, 11, 5),
                                                (48, 48, 513, 3, 1), (24, 24, 4100, 7, 1), (24, 24, 300, 11, 3), (24, 24, 5, 3, 1),
-                                               (96, 96, 13, 3, 1), (64, 128, 257, 3, 1)])
+                                               (96, 96, 13, 3, 1), (64, 128, 257, 3, 1), (12, 12, 700, 7, 3), (40, 24, 300, 3, 1),
+                                               (6, 6, 1500, 11, 5), (96, 96, 30000, 3, 1), (48, 48, 40000, 7, 3),
+                                               (24, 24, 70000, 11, 1), (96, 96, 33000, 11, 5)])
 def test_fused_actconv_equals_unfused(P, Cin, Cout, T, K, dil):
     """The fused Activation1d->conv kernel must reproduce the two-kernel path bit for bit (same stencil,
     same MMA order), including at the sequence edges and across tile boundaries."""

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import index_tts_ipex_b200 as P
 L = P.capi.lib()
-names = ["act_wait_raw", "act_wait_x", "act_busy", "mma_wait_x", "mma_wait_tmem", "mma_total", "epi_wait", "epi_busy"]
+names = ["wk_wait_raw", "wk_wait_x", "wk_stencil", "mma_wait_x", "mma_wait_tmem", "mma_total", "wk_epi_wait", "wk_epi_busy"]
 for (C, T, K, dil, B, res) in [(96, 60160, 3, 1, 32, 0), (96, 60160, 3, 1, 32, 1), (96, 60160, 11, 5, 32, 0), (48, 120320, 3, 1, 32, 0),
                                (24, 240640, 3, 1, 32, 1), (24, 240640, 11, 1, 32, 0)]:
     x = torch.randn(B, C, T, device="cuda").bfloat16()
@@ -19,5 +19,13 @@ for (C, T, K, dil, B, res) in [(96, 60160, 3, 1, 32, 0), (96, 60160, 3, 1, 32, 1
                                             r1.data_ptr() if res else None, 1.0, B, C, C, T, K, dil, torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
     L.bvg_debug_set_umma_counters(None)
+    P.capi.profile_begin()
+    for it in range(3):
+        P.capi.check(L.bvg_actconv_umma_fwd(y.data_ptr(), x.data_ptr(), al.data_ptr(), be.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                            r1.data_ptr() if res else None, 1.0, B, C, C, T, K, dil, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    prof = P.capi.profile_end()
+    ms = prof["conv1d"][0] / 3
+    alg = B * C * T * 2 * (2 + res) / 1e9
     m = dbg.view(148, 8).double().mean(0)
-    print(f"C={C} T={T} K={K} res={res}: " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, m.tolist())))
+    print(f"C={C} T={T} K={K} d={dil} res={res}: {ms*1e3:.0f} us ({alg/ms:.2f} TB/s alg)  " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, m.tolist())))
