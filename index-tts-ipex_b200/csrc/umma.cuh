@@ -61,6 +61,7 @@ struct UmmaConvParams {
   int n_ci_blk, Cin_p, NB, Cout, NPH, MT, tiles_per_batch, zero_pads, tmem_cols;
   int acc_stages, n_nblk, B;
   int x_stages, w_stages, w_resident, kc_max;
+  int a_stages, rows_out;             // fused kernel: A-operand ring depth, output rows per tile (XR - conv halo)
   long long* dbg;
   int dry;
   int n_issuers;

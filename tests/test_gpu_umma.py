@@ -97,8 +97,8 @@ def test_act1d_c8t_vs_oracle(P, Cn, T):
                                                (6, 6, 1500, 11, 5), (96, 96, 30000, 3, 1), (48, 48, 40000, 7, 3),
                                                (24, 24, 70000, 11, 1), (96, 96, 33000, 11, 5)])
 def test_fused_actconv_equals_unfused(P, Cin, Cout, T, K, dil):
-    """The fused Activation1d->conv kernel must reproduce the two-kernel path bit for bit (same stencil,
-    same MMA order), including at the sequence edges and across tile boundaries."""
+    """The fused Activation1d->conv kernel must reproduce the two-kernel path (same stencil, same products; bit for
+    bit when the MMA order is the same), including at the sequence edges and across tile boundaries."""
     gen = torch.Generator().manual_seed(Cin * 3 + T + K)
     B = 2
     x = _bf(torch.randn(B, Cin, T, generator=gen) * 1.5).cuda()
@@ -118,4 +118,12 @@ def test_fused_actconv_equals_unfused(P, Cin, Cout, T, K, dil):
     P.capi.check(L.bvg_actconv_umma_fwd(y.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), w.data_ptr(), bias.data_ptr(),
                                         r1.data_ptr(), 0.5, B, Cin, Cout, T, K, dil, st), "bvg_actconv_umma_fwd")
     torch.cuda.synchronize()
-    assert torch.equal(y, y_ref), float((y.float() - y_ref.float()).abs().max())
+    if Cin <= 48:
+        assert torch.equal(y, y_ref), float((y.float() - y_ref.float()).abs().max())
+    else:
+        # two 48-channel blocks instead of a 64 + 32 split: same products, different fp32 summation order, so a
+        # few outputs may land on the neighbouring bf16 value
+        d = (y.float() - y_ref.float()).abs()
+        mag = torch.maximum(y.float().abs(), y_ref.float().abs())
+        assert float((d - (mag * 2.0 ** -7 + 2e-5)).max()) <= 0, float(d.max())
+        assert float((d > 0).float().mean()) < 0.02
