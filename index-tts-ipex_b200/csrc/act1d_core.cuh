@@ -120,7 +120,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 // bf16x2 word (lo = channel A, hi = channel B) -> (float A, float B)
-__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+// (the low half goes through PRMT so that the shift does not become an IMAD on the FMA pipe, which the stencil saturates)
+__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t w) {
+  uint32_t lo;
+  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(w));
+  return pk2(__uint_as_float(lo), __uint_as_float(w & 0xffff0000u));
+}
 
 // Two signals (channels) at once.  load(j) returns the pair of samples at window position j (= time tg-8+j),
 // j in [3, V+13); store(q, ya, yb) receives output tg+q of both signals.

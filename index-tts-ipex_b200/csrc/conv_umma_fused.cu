@@ -9,9 +9,10 @@
 // *scale -> bf16).  HBM traffic per act+conv pair drops from 5 tensor passes to 2-3.
 //
 // Warp roles (640 threads = 5 warpgroups):
-//   warp 0      TMA producer, raw input rows           warp 3       TMA producer, weights
-//   warps 1-2   MMA issuers (accumulators dealt out)   warps 4-7    epilogue (one per TMEM lane quarter)
-//   warps 8-19  stencil (384 lanes)
+//   warps 0-11  stencil (384 lanes)                    warps 12-15  epilogue (one per TMEM lane quarter)
+//   warp 16     TMA producer, raw input rows           warps 17-18  MMA issuers (accumulators dealt out)
+//   warp 19     TMA producer, weights
+// (the warp scheduler favours high warp ids: the latency-critical roles get them, the stencil fills the rest)
 // The FIR stencil is FMA-pipe bound and is the critical resource, so the geometry is built around it:
 //   * a lane-unit is one 32-bit channel-pair word x 16 rows (21 stencil iterations for 16 outputs); input channels
 //     are processed in blocks of <= 48 (24 words) and an A stage holds XR = 16 * (384 / words) rows INCLUDING the
@@ -40,9 +41,11 @@ namespace bvg {
 namespace {
 
 constexpr int kFThreads = 640;
-constexpr int kFEpiWarp0 = 4;
-constexpr int kFStWarp0 = 8;                  // first stencil warp
-constexpr int kFStWarps = 12;
+// The warp scheduler favours high warp ids, so the latency-critical roles sit at the top: control warpgroup 16-19,
+// epilogue 12-15, and the throughput-bound stencil warps 0-11 soak up whatever issue slots are left.
+constexpr int kFStWarps = 12;                 // stencil warps 0..11
+constexpr int kFEpiWarp0 = 12;                // epilogue warps 12..15 (TMEM lane quarter = warp % 4)
+constexpr int kFCtlWarp0 = 16;                // 16: raw-row producer, 17-18: MMA issuers, 19: weight producer
 constexpr int kFLanes = kFStWarps * 32;       // 384 stencil lanes
 constexpr int kFMaxRaw = 4;                   // raw-input stages (P.x_stages of them are used)
 constexpr int kFMaxA = 4;                     // A-operand stages (P.a_stages)
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], n_iss); mbar_init(&tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kFCtlWarp0 + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(P.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -120,9 +123,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < kFEpiWarp0) {
+  if (warp >= kFCtlWarp0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    if (warp == 0) {
+    if (warp == kFCtlWarp0) {
       // ===================== TMA producer 1: raw input rows (real channel chunks only) =====================
       if (lane == 0) {
         int rs = 0;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
           }
         }
       }
-    } else if (warp == 3) {
+    } else if (warp == kFCtlWarp0 + 3) {
       // ===================== TMA producer 2: weights (own warp: a full weight ring must not delay the raw rows) =====
       // A slot holds one (channel block, tap) tile [chunk][NB][8].  The packed weights are grouped in 64-channel
       // blocks ([cb64][tap][kchunk][NB][8]); a 48-channel block is one or two contiguous runs of that layout.
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       }
     } else {
       // ===================== MMA issuers (as in conv_umma_kernel, conv taps only) =====================
-      const int ii = warp - 1;
+      const int ii = warp - (kFCtlWarp0 + 1);
       if (ii < n_iss) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a_lbo = (uint32_t)XA << 16, b_lbo = (uint32_t)P.NB << 16;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         const int first_tile = blockIdx.x;
         int xs = 0, ws = 0, as = 0;
         uint32_t xph = 0, wph = 0, aph = 0;
-        long long dbg_wx = 0, dbg_wt = 0;
+        long long dbg_wx = 0, dbg_wt = 0, dbg_ww = 0;
         const long long dbg_start = P.dbg ? clock64() : 0;
         for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
           { DBG_T0(); mbar_wait(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }
@@ -205,7 +208,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             for (int tp = 0; tp < P.ntaps; ++tp) {
               const int slot = P.w_resident ? blk * P.ntaps + tp : ws;
               if (!P.w_resident || tile == first_tile) {
+                DBG_T0();
                 mbar_wait(&full_w[slot], P.w_resident ? 0u : wph);
+                DBG_ADD(dbg_ww);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               }
               const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
@@ -233,10 +238,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
           umma_commit_elect(&tmem_full[as]);
           if (++as == 2) { as = 0; aph ^= 1; }
         }
-        if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 8; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; }
+        if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 16; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; d[8] = dbg_ww; }
       }
     }
-  } else if (warp < kFStWarp0) {
+  } else if (warp >= kFEpiWarp0) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
     const int wq = warp & 3;
@@ -273,6 +278,20 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       // the residual rows do not depend on the MMAs: the first slice's loads go out before the wait
       uint4 cur[4], nxt[4];
       load_res(0, 0, cur);
+      if (r1 && tile + (int)gridDim.x < ntiles) {
+        // ... and the rows of this CTA's NEXT tile are pulled into L2 a whole tile ahead, so that the one-slice-ahead
+        // register prefetch only has to cover an L2 hit, not an HBM miss
+        const int nt = tile + gridDim.x;
+        const int nq0 = (nt % P.tiles_per_batch) * P.rows_out;
+        const __nv_bfloat16* nr1 = P.res1 + (int64_t)(nt / P.tiles_per_batch) * P.y_bstride;
+        for (int a = 0; a < nacc; ++a) {
+          const int row = a * 128 + r;
+          if (row < P.rows_out && nq0 + row < P.Tout) {
+            const __nv_bfloat16* rp = nr1 + (P.y_row0 + nq0 + row) * 8;
+            for (int co = 0; co < cout8; co += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (co >> 3) * cs));
+          }
+        }
+      }
       { DBG_T0(); mbar_wait_relaxed(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       DBG_T0();
@@ -335,12 +354,12 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       }
       DBG_ADD(dbg_ebusy);
     }
-    if (P.dbg && threadIdx.x == kFEpiWarp0 * 32) { P.dbg[blockIdx.x * 8 + 6] = dbg_ewait; P.dbg[blockIdx.x * 8 + 7] = dbg_ebusy; }
+    if (P.dbg && threadIdx.x == kFEpiWarp0 * 32) { P.dbg[blockIdx.x * 16 + 6] = dbg_ewait; P.dbg[blockIdx.x * 16 + 7] = dbg_ebusy; }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===================== stencil warps: raw tile -> Activation1d -> A-operand tile =====================
     constexpr int V = kFV;
-    const int L = (warp - kFStWarp0) * 32 + lane;                   // stencil lane 0..383
+    const int L = warp * 32 + lane;                   // stencil lane 0..383
     const int ngroups = P.XR / V;                                   // 16-row groups of the A tile (XR is a multiple of 16)
     int rs = 0, xs = 0;
     uint32_t rph = 0, xph = 0;
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         DBG_T0();
         const uint32_t* raw = reinterpret_cast<const uint32_t*>(rsm + rs * raw_stage_bytes);
         uint32_t* xo = reinterpret_cast<uint32_t*>(xsm + xs * x_stage_bytes);
-        for (int e = L; e < U; e += kFLanes) {
+        for (int e = L; e < (P.dry ? 0 : U); e += kFLanes) {
           const int rg = e / nwords;
           const int wrd = e - rg * nwords;
           const int cg = wrd >> 2, pp = wrd & 3;
@@ -415,11 +434,11 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         if (++xs == nast) { xs = 0; xph ^= 1; }
       }
     }
-    if (P.dbg && threadIdx.x == kFStWarp0 * 32) { long long* d = P.dbg + blockIdx.x * 8; d[0] = dbg_araw; d[1] = dbg_ax; d[2] = dbg_abusy; }
+    if (P.dbg && threadIdx.x == 0) { long long* d = P.dbg + blockIdx.x * 16; d[0] = dbg_araw; d[1] = dbg_ax; d[2] = dbg_abusy; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kFCtlWarp0 + 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols));
   }
@@ -447,6 +466,10 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   if (n_nblk != 1 || P.NB > 128 || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
   P.ntaps = L.K;
   BVG_CHECK_ARG(L.K <= 16, "conv_umma_fused: at most 16 taps");
+  // Wide-and-long layers (C = 96, k = 11) are bound by the number of narrow tcgen05.mma instructions (~100-150 cycles
+  // each whatever N is) rather than by the stencil; in isolation the two-kernel path is faster there, inside the
+  // decode the fused kernel still wins (one tensor pass less through HBM), so the cut-off is off by default.
+  if ((int64_t)((L.Cin + 15) / 16 * 16) * L.K > env_int("BVG_FUSE_MAX_CK", 1 << 30)) return BVG_ERR_STATE;
   const int halo = L.dil * (L.K - 1);
   P.lo = halo / 2;
   BVG_CHECK_ARG(P.lo <= x.pad, "conv_umma_fused: conv padding %d exceeds the c8t halo %d", P.lo, x.pad);
@@ -464,6 +487,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   P.bias = ep.bias; P.scale = ep.scale; P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
   P.act_alpha = act_alpha; P.act_beta = act_beta;
   P.dbg = ep.dbg;
+  P.dry = env_int("BVG_FUSE_DRY", 0);     // experiment: skip the stencil math (timing only, results are garbage)
   P.acc_stages = 2;
   P.n_nblk = 1;
   P.B = (int)B;

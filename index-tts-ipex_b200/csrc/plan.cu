@@ -402,11 +402,10 @@ int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, in
                             L.Cout, T, L.K, dil, 0, dtype, dtype, st);
 }
 
-// BVG_FUSE=1 routes AMPBlock1's act->conv pairs of the narrow stages through conv_umma_fused_kernel (one kernel,
-// activated tensor never in HBM).  Bit-identical to the two-kernel path, but measured slower so far (87.6 vs 64.3 ms
-// per benchmark step): the FIR stencil is FMA-pipe bound and a fused CTA holds 12 stencil warps against the
-// standalone kernel's 16, and the raw-tile pipeline is too shallow; see DESIGN.md §4.  Off by default.
-const bool g_fuse_act = [] { const char* e = getenv("BVG_FUSE"); return e && e[0] == '1'; }();
+// AMPBlock1's act->conv pairs of the narrow stages run as one kernel (conv_umma_fused_kernel: the activated tensor
+// never exists in HBM); layers that do not qualify fall back to the Activation1d kernel + conv kernel.
+// BVG_FUSE=0 forces the two-kernel path everywhere (A/B measurements, tests).
+const bool g_fuse_act = [] { const char* e = getenv("BVG_FUSE"); return !(e && e[0] == '0'); }();
 
 UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1) {
   UmmaLayer u;
