@@ -47,25 +47,47 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-def algorithmic_work(h, B, T0_):
-    """FLOPs of all dense convs and Activation1d bytes (2*B*C*T*sizeof) per step."""
+FUSED_MAX_C = 128      # AMPBlock1 act->conv pairs with C <= 128 run as one fused kernel (conv_umma_fused.cu)
+# dram__bytes_read.sum + dram__bytes_write.sum per fused launch, averaged over the 54 fused launches of one benchmark
+# step (ncu capture of tools/prof_decode.py; see the named file)
+FUSED_TRAFFIC_PER_LAUNCH = None
+FUSED_TRAFFIC_NOTE = "not captured yet"
+
+
+def algorithmic_work(h, B, T0_, es=2, fused=True):
+    """Algorithmic work of one step: FLOPs of the dense convs, bytes of the Activation1d passes
+    (2*B*C*T*es each) and of the fused Activation1d->conv launches (input + output [+ residuals] + weights)."""
     C0 = h.upsample_initial_channel
-    conv_mac = C0 * h.gpt_dim * 7 * T0_
+    conv_mac = C0 * h.gpt_dim * 7 * T0_            # conv_pre
+    fused_mac = 0
     convtr_mac = 0
-    act_elems = 0
+    act_elems = 0                                   # standalone Activation1d launches only
+    fused_bytes = 0.0
+    fused_launches = 0
     T = T0_
+    nk = len(h.resblock_kernel_sizes)
     for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
         cin, cout = C0 >> i, C0 >> (i + 1)
         convtr_mac += cin * cout * k * T
         T *= u
-        for rk in h.resblock_kernel_sizes:
-            conv_mac += 6 * cout * cout * rk * T
-            act_elems += 6 * cout * T
+        for j, rk in enumerate(h.resblock_kernel_sizes):
+            mac = 6 * cout * cout * rk * T
+            if fused and cout <= FUSED_MAX_C:
+                fused_mac += mac
+                fused_launches += 6
+                # 3 x c1 (read x, write xt) + 3 x c2 (read xt, read the residual, write); the last c2 of resblocks
+                # 2.. also reads the running sum
+                passes = 3 * 2 + 3 * 3 + (1 if j > 0 else 0)
+                fused_bytes += passes * cout * T * es * B + 6 * cout * cout * rk * 2
+            else:
+                conv_mac += mac
+                act_elems += 6 * cout * T
     cp = C0 >> len(h.upsample_rates)
     act_elems += cp * T
     post_mac = cp * 7 * T
-    return dict(conv_flops=2.0 * conv_mac * B, convtr_flops=2.0 * convtr_mac * B, post_flops=2.0 * post_mac * B,
-                act_elems=float(act_elems) * B)
+    return dict(conv_flops=2.0 * conv_mac * B, fused_flops=2.0 * fused_mac * B, convtr_flops=2.0 * convtr_mac * B,
+                post_flops=2.0 * post_mac * B, act_elems=float(act_elems) * B, fused_bytes=fused_bytes,
+                fused_launches=fused_launches, nk=nk)
 
 
 class ClockSampler:
@@ -261,25 +283,36 @@ def run_ours(args):
         m.decode(lat, mel_ref=mel)
     prof = pkg.capi.profile_end()
     if rank == 0:
-        work = algorithmic_work(h, B, T0)
-        pk = peaks()
         es = 2 if args.precision == "bf16" else 4
+        fused_on = args.precision == "bf16" and os.environ.get("BVG_FUSE", "1") != "0"
+        work = algorithmic_work(h, B, T0, es, fused_on)
+        pk = peaks()
         per_step = {k: (v[0] / n_prof, v[1] // n_prof) for k, v in prof.items()}
         kernel_ms = sum(v[0] for v in per_step.values())
         dom = max(per_step, key=lambda k: per_step[k][0])
         conv_ms, conv_n = per_step["conv1d"]
         act_ms, act_n = per_step["act1d"]
+        fus_ms, fus_n = per_step["actconv"]
         conv_tf = work["conv_flops"] / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         act_gbs = 2.0 * work["act_elems"] * es / (act_ms / 1e3) / 1e9 if act_ms > 0 else 0.0
-        if dom == "act1d":
-            roof = {"kernel": "act1d_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
+        fus_gbs = work["fused_bytes"] / (fus_ms / 1e3) / 1e9 if fus_ms > 0 else 0.0
+        if fus_n and fus_n != work["fused_launches"]:
+            print(f"bench: warning: {fus_n} fused launches, accounting expects {work['fused_launches']}", file=sys.stderr)
+        if dom == "actconv":
+            # algorithmic bytes per launch / average launch time; traffic = ncu dram bytes per launch (same step)
+            roof = {"kernel": "conv_umma_fused_kernel (Activation1d -> Conv1d, narrow stages)", "bound": "hbm",
+                    "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": fus_gbs / pk["hbm"],
+                    "traffic": FUSED_TRAFFIC_PER_LAUNCH, "algorithmic_bytes_per_launch": work["fused_bytes"] / max(fus_n, 1),
+                    "traffic_note": FUSED_TRAFFIC_NOTE,
+                    "limiter": "FMA pipe (the 12+12-tap FIR stencil), not HBM: see profiles/README.md"}
+        elif dom == "act1d":
+            roof = {"kernel": "act1d_c8t_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": act_gbs / pk["hbm"], "traffic": None}
         else:
-            roof = {"kernel": "conv_umma_kernel (all dense generator convs of the step)", "bound": "tensor",
+            roof = {"kernel": "conv_umma_kernel (dense generator convs outside the fused stages)", "bound": "tensor",
                     "achieved": conv_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": conv_tf / pk["tf_sustained"], "traffic": None,
-                    "traffic_note": "per-launch DRAM bytes of representative launches are in profiles/r01_ncu_full_summary.txt "
-                                    "(C=96 k=3: 688 MB measured vs 740 MB algorithmic)"}
+                    "traffic_note": "per-launch DRAM bytes of representative launches are in profiles/r01_ncu_full_summary.txt"}
         roof["peak_source"] = pk["src"] + (" sustained" if roof["bound"] == "tensor" else " copy")
         roof["launches_per_step"] = per_step[dom][1]
         roof["avg_launch_ms"] = per_step[dom][0] / max(per_step[dom][1], 1)
@@ -297,6 +330,9 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "kernel_classes_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in per_step.items()},
+            "roofline_actconv": {"bound": "hbm", "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                 "frac": fus_gbs / pk["hbm"], "bytes_per_step": work["fused_bytes"],
+                                 "flops_per_step": work["fused_flops"], "launches_per_step": fus_n},
             "roofline_act1d": {"bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": act_gbs / pk["hbm"], "bytes_per_step": 2.0 * work["act_elems"] * es,
                                "launches_per_step": act_n},

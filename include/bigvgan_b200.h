@@ -57,7 +57,8 @@ BVG_API void bvg_launch_count_reset(void);
    kernel launched from the calling thread is bracketed by CUDA events on its stream.
    bvg_profile_end synchronises those events and returns, per class, the summed kernel time (ms)
    and the launch count.  Classes: 0 Activation1d, 1 dense Conv1d (generator), 2 ConvTranspose1d,
-   3 everything else (speaker encoder, cond vectors, conv_post).  Arrays have 4 entries. */
+   3 everything else (speaker encoder, cond vectors, conv_post), 4 fused Activation1d->Conv1d
+   (narrow generator stages).  Arrays have 5 entries. */
 BVG_API void bvg_profile_begin(void);
 BVG_API int bvg_profile_end(float* ms_per_class, int64_t* launches_per_class);
 

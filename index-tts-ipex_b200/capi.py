@@ -104,7 +104,7 @@ def launch_count_reset() -> None:
     lib().bvg_launch_count_reset()
 
 
-KERNEL_CLASSES = ("act1d", "conv1d", "convtr1d", "other")
+KERNEL_CLASSES = ("act1d", "conv1d", "convtr1d", "other", "actconv")
 
 
 def profile_begin() -> None:
@@ -113,7 +113,7 @@ def profile_begin() -> None:
 
 def profile_end():
     """-> {class: (ms, launches)} for kernels launched since profile_begin()."""
-    ms = (C.c_float * 4)()
-    n = (C.c_int64 * 4)()
+    ms = (C.c_float * len(KERNEL_CLASSES))()
+    n = (C.c_int64 * len(KERNEL_CLASSES))()
     check(lib().bvg_profile_end(ms, n), "bvg_profile_end")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}

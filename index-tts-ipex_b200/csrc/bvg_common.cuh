@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...);
 extern thread_local int64_t g_launches;
 
 // ---- optional per-kernel-class timing (bvg_profile_*): CUDA events around every launch ---------
-enum KernelClass { KC_ACT1D = 0, KC_CONV = 1, KC_CONVTR = 2, KC_OTHER = 3, KC_COUNT = 4 };
+enum KernelClass { KC_ACT1D = 0, KC_CONV = 1, KC_CONVTR = 2, KC_OTHER = 3, KC_ACTCONV = 4, KC_COUNT = 5 };
 void prof_mark(cudaStream_t st, int kclass, bool begin);
 struct ProfScope {
   cudaStream_t st;

@@ -57,6 +57,79 @@ __host__ __device__ inline size_t fused_fixed_smem(int NB, int Cin_p) {
   return (size_t)(2 * kFMaxRaw + 2 * kFMaxA + 2 * kFMaxW + 4) * 8 + 16 + (size_t)NB * 4 + (size_t)Cin_p * 8;
 }
 
+// Epilogue of one tile for one epilogue warp (TMEM lane quarter wq): accumulator slices of NCH 8-channel chunks
+// -> (+bias) (+res1) (+res2) (*scale) -> bf16 -> 16-byte stores.  Residual slices are register-prefetched one slice
+// ahead (their rows were pulled into L2 a tile ahead by the caller), the first slice before the wait for the MMAs.
+// HAS_R2 (the last conv of resblocks 2.. adds the running sum as a second residual) uses 16-column slices so that two
+// residual streams fit the register budget.
+template <int NCH, bool HAS_R2>
+__device__ __forceinline__ void fused_epilogue_tile(const UmmaConvParams& P, __nv_bfloat16* yb, const __nv_bfloat16* r1,
+                                                    const __nv_bfloat16* r2, const float* bias_s, uint32_t tbase, int q0, int r,
+                                                    int nacc, uint64_t* tmem_full_bar, uint32_t aph, long long& dbg_ewait) {
+  constexpr int W = 8 * NCH;                                        // columns per slice
+  const int nsl = (P.NB + W - 1) / W;                               // slices per accumulator (the last may be narrower)
+  const int cs = P.y_tp * 8;                                        // elements between channel chunks
+  const int cout8 = (P.Cout + 7) & ~7, ych8 = P.y_chunks * 8;
+  const float scale = P.scale;
+  // element offset (within the batch element) of accumulator row `a`, chunk 0; -1 if the row is not an output
+  auto row_off = [&](int a) -> int {
+    const int row = a * 128 + r;
+    return (a < nacc && row < P.rows_out && q0 + row < P.Tout) ? (P.y_row0 + q0 + row) * 8 : -1;
+  };
+  auto load_res = [&](const __nv_bfloat16* rp, int a, int si, uint4 (&e)[NCH]) {
+    const int ro = rp ? row_off(a) : -1;
+#pragma unroll
+    for (int g = 0; g < NCH; ++g) {
+      const int co = si * W + 8 * g;
+      e[g] = (ro >= 0 && co < cout8) ? *reinterpret_cast<const uint4*>(rp + ro + (co >> 3) * cs) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 cur1[NCH], nxt1[NCH], cur2[HAS_R2 ? NCH : 1], nxt2[HAS_R2 ? NCH : 1];
+  load_res(r1, 0, 0, cur1);
+  if (HAS_R2) load_res(r2, 0, 0, *reinterpret_cast<uint4(*)[NCH]>(&cur2[0]));
+  { DBG_T0(); mbar_wait_relaxed(tmem_full_bar, aph); DBG_ADD(dbg_ewait); }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int a = 0, si = 0; a < nacc;) {
+    int na = a, nsi = si + 1;
+    if (nsi == nsl) { nsi = 0; ++na; }
+    load_res(r1, na, nsi, nxt1);                                    // next slice's residuals overlap this slice's TMEM reads
+    if (HAS_R2) load_res(r2, na, nsi, *reinterpret_cast<uint4(*)[NCH]>(&nxt2[0]));
+    const int c0 = si * W;
+    const bool wide = NCH == 4 && c0 + 16 < P.NB;                   // a 32-column slice may be cut to 16 at the end
+    uint32_t v[W];
+    tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    if (NCH == 4 && wide) tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[W - 16]));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int ro = row_off(a);
+    if (ro >= 0) {
+#pragma unroll
+      for (int g = 0; g < NCH; ++g) {
+        const int co = c0 + 8 * g;
+        if ((g >= 2 && !wide) || co >= ych8) continue;              // (padding channels inside the tensor become zeros)
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[co + j];
+        if (r1) { float ee[8]; unpack8(cur1[g], ee);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += ee[j]; }
+        if (HAS_R2) { float ee[8]; unpack8(cur2[HAS_R2 ? g : 0], ee);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += ee[j]; }
+        uint4 o;
+        o.x = pack2(f[0] * scale, f[1] * scale); o.y = pack2(f[2] * scale, f[3] * scale);
+        o.z = pack2(f[4] * scale, f[5] * scale); o.w = pack2(f[6] * scale, f[7] * scale);
+        *reinterpret_cast<uint4*>(yb + ro + (co >> 3) * cs) = o;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < NCH; ++g) {
+      cur1[g] = nxt1[g];
+      if (HAS_R2) cur2[HAS_R2 ? g : 0] = nxt2[HAS_R2 ? g : 0];
+    }
+    a = na; si = nsi;
+  }
+}
+
 __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const UmmaConvParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -246,14 +319,28 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
     // ===================== epilogue (4 warps, one per TMEM lane quarter) =====================
     const int wq = warp & 3;
     const int r = wq * 32 + lane;                                   // accumulator row
-    const int ngrp16 = P.NB >> 4;
-    const int npair = (ngrp16 + 1) >> 1;                            // 32-column slices per accumulator (the last may be 16 wide)
     const int cs = P.y_tp * 8;                                      // elements between channel chunks
-    const int cout8 = (P.Cout + 7) & ~7, ych8 = P.y_chunks * 8;
-    const float scale = P.scale;
+    const int cout8 = (P.Cout + 7) & ~7;
     int as = 0;
     uint32_t aph = 0;
     long long dbg_ewait = 0, dbg_ebusy = 0;
+    // pull the residual rows of a tile into L2 (one prefetch per 16-byte chunk row of this lane's accumulator rows)
+    auto l2_prefetch_tile = [&](int t) {
+      if (t >= ntiles || !(P.res1 || P.res2)) return;
+      const int nq0 = (t % P.tiles_per_batch) * P.rows_out;
+      const int64_t boff = (int64_t)(t / P.tiles_per_batch) * P.y_bstride;
+      for (int a = 0; a < nacc; ++a) {
+        const int row = a * 128 + r;
+        if (row < P.rows_out && nq0 + row < P.Tout) {
+          const int64_t ro = boff + (P.y_row0 + nq0 + row) * 8;
+          for (int co = 0; co < cout8; co += 8) {
+            if (P.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res1 + ro + (co >> 3) * cs));
+            if (P.res2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res2 + ro + (co >> 3) * cs));
+          }
+        }
+      }
+    };
+    l2_prefetch_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mt = tile % P.tiles_per_batch;
       const int b = tile / P.tiles_per_batch;
@@ -261,80 +348,14 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
       const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
-      // element offset (within the batch element) of accumulator row `a`, chunk 0; -1 if the row is not an output
-      auto row_off = [&](int a) -> int {
-        const int row = a * 128 + r;
-        return (a < nacc && row < P.rows_out && q0 + row < P.Tout) ? (P.y_row0 + q0 + row) * 8 : -1;
-      };
-      // residual slice (32 columns = 4 chunks) of accumulator a, pair pi
-      auto load_res = [&](int a, int pi, uint4 (&e)[4]) {
-        const int ro = r1 ? row_off(a) : -1;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int co = pi * 32 + 8 * g;
-          e[g] = (ro >= 0 && co < cout8) ? *reinterpret_cast<const uint4*>(r1 + ro + (co >> 3) * cs) : make_uint4(0, 0, 0, 0);
-        }
-      };
-      // the residual rows do not depend on the MMAs: the first slice's loads go out before the wait
-      uint4 cur[4], nxt[4];
-      load_res(0, 0, cur);
-      if (r1 && tile + (int)gridDim.x < ntiles) {
-        // ... and the rows of this CTA's NEXT tile are pulled into L2 a whole tile ahead, so that the one-slice-ahead
-        // register prefetch only has to cover an L2 hit, not an HBM miss
-        const int nt = tile + gridDim.x;
-        const int nq0 = (nt % P.tiles_per_batch) * P.rows_out;
-        const __nv_bfloat16* nr1 = P.res1 + (int64_t)(nt / P.tiles_per_batch) * P.y_bstride;
-        for (int a = 0; a < nacc; ++a) {
-          const int row = a * 128 + r;
-          if (row < P.rows_out && nq0 + row < P.Tout) {
-            const __nv_bfloat16* rp = nr1 + (P.y_row0 + nq0 + row) * 8;
-            for (int co = 0; co < cout8; co += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (co >> 3) * cs));
-          }
-        }
-      }
-      { DBG_T0(); mbar_wait_relaxed(&tmem_full[as], aph); DBG_ADD(dbg_ewait); }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the residual rows of this CTA's NEXT tile go to L2 a whole tile ahead, so that the one-slice-ahead register
+      // prefetch only has to cover an L2 hit, not an HBM miss
+      l2_prefetch_tile(tile + gridDim.x);
       DBG_T0();
+      const long long ew0 = dbg_ewait;
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
-      for (int a = 0, pi = 0; a < nacc;) {
-        int na = a, npi = pi + 1;
-        if (npi == npair) { npi = 0; ++na; }
-        load_res(na, npi, nxt);                                     // next slice's residuals overlap this slice's TMEM reads
-        const int c0 = pi * 32;
-        const bool wide = c0 + 16 < P.NB;
-        uint32_t v[32];
-        tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (wide) tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int ro = row_off(a);
-        if (ro >= 0) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int co = c0 + 8 * g;
-            if ((g >= 2 && !wide) || co >= ych8) continue;          // (padding channels inside the tensor become zeros)
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + co), b1 = *reinterpret_cast<const float4*>(bias_s + co + 4);
-            float f[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += __uint_as_float(v[8 * g + j]);
-            if (r1) { float ee[8]; unpack8(cur[g], ee);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += ee[j]; }
-            if (r2 && co < cout8) {
-              float ee[8];
-              unpack8(*reinterpret_cast<const uint4*>(r2 + ro + (co >> 3) * cs), ee);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += ee[j];
-            }
-            uint4 o;
-            o.x = pack2(f[0] * scale, f[1] * scale); o.y = pack2(f[2] * scale, f[3] * scale);
-            o.z = pack2(f[4] * scale, f[5] * scale); o.w = pack2(f[6] * scale, f[7] * scale);
-            *reinterpret_cast<uint4*>(yb + ro + (co >> 3) * cs) = o;
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
-        a = na; pi = npi;
-      }
+      if (r2) fused_epilogue_tile<2, true>(P, yb, r1, r2, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait);
+      else fused_epilogue_tile<4, false>(P, yb, r1, nullptr, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait);
       // all of this warp's TMEM reads for the stage are complete: hand it back to the MMA issuers
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -353,6 +374,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
       }
       DBG_ADD(dbg_ebusy);
+      dbg_ebusy -= dbg_ewait - ew0;
     }
     if (P.dbg && threadIdx.x == kFEpiWarp0 * 32) { P.dbg[blockIdx.x * 16 + 6] = dbg_ewait; P.dbg[blockIdx.x * 16 + 7] = dbg_ebusy; }
   } else {
@@ -548,7 +570,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
     BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
-  ProfScope prof(st, KC_CONV);
+  ProfScope prof(st, KC_ACTCONV);
   conv_umma_fused_kernel<<<grid, kFThreads, smem, st>>>(P);
   BVG_LAUNCHED();
   return BVG_OK;

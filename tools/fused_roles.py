@@ -25,7 +25,7 @@ for (C, T, K, dil, B, res) in [(96, 60160, 3, 1, 32, 0), (96, 60160, 3, 1, 32, 1
                                             r1.data_ptr() if res else None, 1.0, B, C, C, T, K, dil, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     prof = P.capi.profile_end()
-    ms = prof["conv1d"][0] / 3
+    ms = prof["actconv"][0] / 3
     alg = B * C * T * 2 * (2 + res) / 1e9
     m = dbg.view(148, 16).double().mean(0)
     print(f"C={C} T={T} K={K} d={dil} res={res}: {ms*1e3:.0f} us ({alg/ms:.2f} TB/s alg)  " + "  ".join(f"{n}={v/1e3:.0f}k" for n, v in zip(names, m.tolist())))
