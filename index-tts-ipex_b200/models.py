@@ -359,9 +359,11 @@ class BigVGAN(nn.Module):
         return wav, None
 
     @torch.no_grad()
-    def decode_host(self, latent_cpu, mel_cpu, device, pcm16=False):
+    def decode_host(self, latent_cpu, mel_cpu, device, pcm16=False, out=None):
         """End-to-end call with HOST tensors (pinned for async copies): H2D, decode, D2H inside
-        the library (bvg_decode_host).  Returns a pinned CPU tensor."""
+        the library (bvg_decode_host).  Returns a pinned CPU tensor; pass a pinned `out` of the right shape
+        ([B, 1, T0*1024] fp32, or [B, T0*1024] int16 with pcm16) to reuse it across calls -- allocating pinned
+        memory costs more than the copies themselves."""
         device = torch.device(device)
         plan = self._ensure_plan(device)
         lat = latent_cpu.to(torch.float32).contiguous()
@@ -372,12 +374,12 @@ class BigVGAN(nn.Module):
         L = T0 * self.total_upsample
         nbytes = int(capi.lib().bvg_workspace_bytes(plan, B, T0, Tm, code))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        if pcm16:
-            out = torch.empty(B, L, dtype=torch.int16, pin_memory=True)
-            wav_ptr, pcm_ptr = None, out.data_ptr()
-        else:
-            out = torch.empty(B, 1, L, dtype=torch.float32, pin_memory=True)
-            wav_ptr, pcm_ptr = out.data_ptr(), None
+        shape, dt = ((B, L), torch.int16) if pcm16 else ((B, 1, L), torch.float32)
+        if out is None:
+            out = torch.empty(shape, dtype=dt, pin_memory=True)
+        elif tuple(out.shape) != shape or out.dtype != dt or out.device.type != "cpu" or not out.is_contiguous():
+            raise RuntimeError(f"decode_host: out must be a contiguous CPU {dt} tensor of shape {shape}")
+        wav_ptr, pcm_ptr = (None, out.data_ptr()) if pcm16 else (out.data_ptr(), None)
         with torch.cuda.device(device):
             st = torch.cuda.current_stream().cuda_stream
             capi.check(capi.lib().bvg_decode_host(plan, lat.data_ptr(), mel.data_ptr(), B, T0, Bm, Tm, code, wav_ptr,
