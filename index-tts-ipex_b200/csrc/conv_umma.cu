@@ -47,7 +47,9 @@ constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 // mainloop of tile i+1 whenever two accumulator stages fit in TMEM.
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role-dependent values such as the MMA descriptors
+  // then stay in uniform registers instead of being broadcast out of a lane before every tcgen05.mma)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   const int kXStages = P.x_stages, kWStages = P.w_stages;
@@ -142,23 +144,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     // The issue path between two MMAs must stay well under the ~54-cycle execution time of a small-N MMA.
     const int ii = warp - 1;
     if (ii < P.n_issuers) {
-      // Everything the loop needs is pinned in registers (the empty asm hides the values from constant
-      // re-materialisation): a kernel-parameter reload (LDCU) between two MMAs costs more than a narrow MMA takes.
-#define PIN(v) asm volatile("" : "+r"(v))
+      // The whole warp runs this loop on warp-uniform values: descriptor words live in uniform registers, advance with
+      // uniform adds and feed tcgen05.mma directly (no per-lane broadcast); one elected lane issues.
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = NB, M = 128
-      uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
       // smem descriptors (K-major, no swizzle): lo word = start>>4 | (LBO>>4)<<16, hi word = SBO>>4 | version
-      uint32_t a_lbo = (uint32_t)P.XR << 16, b_lbo = (uint32_t)P.NB << 16;
-      uint32_t astep = 2u * P.XR, bstep = 2u * P.NB;                 // 16 input channels further along K
-      int NB = P.NB, MT = P.MT, NPH = P.NPH, dil = P.dil, n_iss = P.n_issuers, ntaps = P.ntaps;
-      int n_ci_blk = P.n_ci_blk, Cin_p = P.Cin_p, resident = P.w_resident, dry = P.dry, transposed = P.transposed;
-      int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols;
-      uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
-      uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
-      PIN(idesc); PIN(astep); PIN(bstep); PIN(NB); PIN(MT); PIN(NPH); PIN(dil); PIN(n_iss); PIN(ntaps);
-      PIN(n_ci_blk); PIN(Cin_p); PIN(resident); PIN(dry); PIN(transposed); PIN(n_xst); PIN(n_wst); PIN(n_ast);
-      PIN(acols); PIN(xsb16); PIN(wslot16); PIN(x_base); PIN(w_base);
-#undef PIN
+      const uint32_t a_lbo = (uint32_t)P.XR << 16, b_lbo = (uint32_t)P.NB << 16;
+      const uint32_t astep = 2u * P.XR, bstep = 2u * P.NB;            // 16 input channels further along K
+      const int NB = P.NB, MT = P.MT, NPH = P.NPH, dil = P.dil, n_iss = P.n_issuers, ntaps = P.ntaps;
+      const int n_ci_blk = P.n_ci_blk, Cin_p = P.Cin_p, resident = P.w_resident, dry = P.dry, transposed = P.transposed;
+      const int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols;
+      const uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
+      const uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
       const int first_tile = blockIdx.x;
       int xs = 0, ws = 0, as = 0;
       uint32_t xph = 0, wph = 0, aph = 0;
@@ -182,28 +179,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             }
             const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
             const uint32_t accum0 = (cb > 0 || tp >= NPH) ? 1u : 0u;  // taps 0..NPH-1 are the first to touch their accumulator
-            if (lane == 0) {
-              if (!transposed) {
-                // conv: tap = row shift tp*dil; issuer ii owns time sub-tiles ms = ii, ii + n_issuers, ...
-                const uint32_t a_tp = a_cb + (uint32_t)(tp * dil);
-                for (int ms = ii; ms < MT; ms += n_iss) {
-                  const uint32_t d = dbase + (uint32_t)(ms * NB);
-                  uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
-                  umma_bf16_imm(d, am, bm, idesc, accum0);
-                  for (int k = 1; k < nk; ++k) {
-                    am += astep; bm += bstep;
-                    umma_bf16_imm(d, am, bm, idesc, 1u);
-                  }
-                }
-              } else if ((P.tap_acc[tp] & (n_iss - 1)) == ii) {
-                // ConvTranspose: one accumulator per output phase, issuer ii owns phases == ii (mod n_issuers)
-                const uint32_t d = dbase + (uint32_t)(P.tap_acc[tp] * NB);
-                uint32_t am = a_cb + (uint32_t)P.tap_shift[tp], bm = b_lo;
-                umma_bf16_imm(d, am, bm, idesc, accum0);
+            if (!transposed) {
+              // conv: tap = row shift tp*dil; issuer ii owns time sub-tiles ms = ii, ii + n_issuers, ...
+              const uint32_t a_tp = a_cb + (uint32_t)(tp * dil);
+              for (int ms = ii; ms < MT; ms += n_iss) {
+                const uint32_t d = dbase + (uint32_t)(ms * NB);
+                uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
+                umma_bf16_imm_elect(d, am, bm, idesc, accum0);
                 for (int k = 1; k < nk; ++k) {
                   am += astep; bm += bstep;
-                  umma_bf16_imm(d, am, bm, idesc, 1u);
+                  umma_bf16_imm_elect(d, am, bm, idesc, 1u);
                 }
+              }
+            } else if ((P.tap_acc[tp] & (n_iss - 1)) == ii) {
+              // ConvTranspose: one accumulator per output phase, issuer ii owns phases == ii (mod n_issuers)
+              const uint32_t d = dbase + (uint32_t)(P.tap_acc[tp] * NB);
+              uint32_t am = a_cb + (uint32_t)P.tap_shift[tp], bm = b_lo;
+              umma_bf16_imm_elect(d, am, bm, idesc, accum0);
+              for (int k = 1; k < nk; ++k) {
+                am += astep; bm += bstep;
+                umma_bf16_imm_elect(d, am, bm, idesc, 1u);
               }
             }
             if (!resident && !dry) {

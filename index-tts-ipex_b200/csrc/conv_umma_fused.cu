@@ -132,7 +132,9 @@ __device__ __forceinline__ void fused_epilogue_tile(const UmmaConvParams& P, __n
 
 __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const UmmaConvParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
+  // (the shuffle tells the compiler the warp index is warp-uniform: role-dependent values such as the MMA descriptors
+  // can then stay in uniform registers instead of being broadcast out of a lane before every tcgen05.mma)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   const int nraw = P.x_stages, nast = P.a_stages, kWStages = P.w_stages;
@@ -288,16 +290,15 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
               }
               const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
               const uint32_t accum0 = (blk > 0 || tp > 0) ? 1u : 0u;
-              if (lane == 0) {
+              {
+                // the whole (converged) warp runs the loop on warp-uniform values; one elected lane issues
                 const uint32_t a_tp = a_cb + (uint32_t)(tp * P.dil);
                 for (int ms = ii; ms < nacc; ms += n_iss) {
                   const uint32_t d = dbase + (uint32_t)(ms * P.NB);
-                  uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
-                  umma_bf16_imm(d, am, bm, idesc, accum0);
-                  for (int k = 1; k < nk; ++k) {
-                    am += astep; bm += bstep;
-                    umma_bf16_imm(d, am, bm, idesc, 1u);
-                  }
+                  const uint32_t am = a_tp + (uint32_t)(ms * 128);
+                  umma_bf16_imm_elect(d, am, b_lo, idesc, accum0);
+                  if (nk > 1) umma_bf16_imm_elect(d, am + astep, b_lo + bstep, idesc, 1u);
+                  if (nk > 2) umma_bf16_imm_elect(d, am + 2 * astep, b_lo + 2 * bstep, idesc, 1u);
                 }
               }
               if (!P.w_resident) {

@@ -108,6 +108,18 @@ __device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with the election inside: executed by a fully converged warp with warp-uniform operands, so the
+// operands can live in uniform registers and no per-lane broadcast loop is generated around the instruction
+__device__ __forceinline__ void umma_bf16_imm_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p, e;\n.reg .b64 da, db;\n"
+      "mov.b64 da, {%1, 0x4008};\nmov.b64 db, {%2, 0x4008};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
