@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 // Thread = one 32-bit word (2 channels) x 16 consecutive rows; warp = 4 words x NCH chunks x (8/NCH) row groups.
 template <int NCH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                  const float* __restrict__ alpha_log, const float* __restrict__ beta_log, int C, int chunks, int T,
                  int Tp, int pad) {
