@@ -49,11 +49,14 @@ __device__ __forceinline__ float final_act(float v, int act) {
   return v;
 }
 
-template <typename TI, typename TO>
+// NT = accumulators per thread and dimension: 8 -> the 128 x 128 tile above, 4 -> a 64 x 64 tile for the small layers
+// of the speaker encoder (Res2Net 64 -> 64 convs over 281 frames: four times as many CTAs, a quarter of the serial work)
+template <typename TI, typename TO, int NT>
 __global__ void __launch_bounds__(256)
 conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src, const TI* __restrict__ src2,
                    int64_t sb, int64_t sc, int64_t st_, const float* __restrict__ w, EpiDev ep,
                    int64_t Cin, int64_t Cout, int64_t T, int K, int dil, int pad_mode) {
+  constexpr int kTT = 16 * NT, kTC = 16 * NT, kXW = kTT + kMaxHalo;
   __shared__ float xs[kCK][kXW];
   __shared__ __align__(16) float ws[kCK][kTC];
 
@@ -65,11 +68,11 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
   const int pad = dil * (K - 1) / 2;
   const int xw = kTT + dil * (K - 1);
 
-  float acc[8][8];
+  float acc[NT][NT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < NT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
 
   const TI* sbase = src + b * sb;
   const TI* sbase2 = src2 ? src2 + b * sb : nullptr;
@@ -98,7 +101,7 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
       if (k) __syncthreads();
       const float* wk = w + ((int64_t)k * Cin + ci0) * Cout + co0;
       for (int idx = tid; idx < kCK * kTC; idx += 256) {
-        const int ci = idx >> 7, c = idx & 127;
+        const int ci = idx / kTC, c = idx % kTC;
         float v = 0.f;
         if (ci0 + ci < Cin && co0 + c < Cout) v = wk[(int64_t)ci * Cout + c];
         ws[ci][c] = v;
@@ -107,16 +110,19 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
       const int shift = k * dil + tx;
 #pragma unroll 4
       for (int ci = 0; ci < kCK; ++ci) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&ws[ci][ty * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&ws[ci][ty * 8 + 4]);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        float xv[8];
+        float wv[NT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = xs[ci][shift + 16 * j];
+        for (int i = 0; i < NT; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[ci][ty * NT + i]);
+          wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+        }
+        float xv[NT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < NT; ++j) xv[j] = xs[ci][shift + 16 * j];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
       }
     }
   }
@@ -125,11 +131,11 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
   const TO* r1 = ep.res1 ? static_cast<const TO*>(ep.res1) + b * dsb : nullptr;
   const TO* r2 = ep.res2 ? static_cast<const TO*>(ep.res2) + b * dsb : nullptr;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t co = co0 + ty * 8 + i;
+  for (int i = 0; i < NT; ++i) {
+    const int64_t co = co0 + ty * NT + i;
     if (co >= Cout) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const int64_t t = t0 + tx + 16 * j;
       if (t >= T) continue;
       float v = epilogue_apply(acc[i][j], ep, b, co, Cout);
@@ -153,6 +159,7 @@ convtr1d_simt_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const flo
   __shared__ float xs[kCK][kXI];
   __shared__ __align__(16) float ws[kCK][kTC];
 
+  constexpr int NT = 8;     // 8 x 8 accumulators per thread (128 x 128 tile)
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t Tout = Tin * u;
@@ -166,11 +173,11 @@ convtr1d_simt_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const flo
   const int64_t i_hi = (t0 + kTT - 1 + p) / u;
   const int ni = (int)(i_hi - i_lo + 1);
 
-  float acc[8][8];
+  float acc[NT][NT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < NT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
 
   const TT* sbase = src + b * Cin * Tin;
   for (int64_t ci0 = 0; ci0 < Cin; ci0 += kCK) {
@@ -186,7 +193,7 @@ convtr1d_simt_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const flo
       if (k) __syncthreads();
       const float* wk = w + ((int64_t)k * Cin + ci0) * Cout + co0;
       for (int idx = tid; idx < kCK * kTC; idx += 256) {
-        const int ci = idx >> 7, c = idx & 127;
+        const int ci = idx / kTC, c = idx % kTC;
         float v = 0.f;
         if (ci0 + ci < Cin && co0 + c < Cout) v = wk[(int64_t)ci * Cout + c];
         ws[ci][c] = v;
@@ -222,11 +229,11 @@ convtr1d_simt_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const flo
   }
   TT* dbase = dst + b * Cout * Tout;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int64_t co = co0 + ty * 8 + i;
+  for (int i = 0; i < NT; ++i) {
+    const int64_t co = co0 + ty * NT + i;
     if (co >= Cout) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const int64_t t = t0 + tx + 16 * j;
       if (t >= Tout) continue;
       float v = epilogue_apply(acc[i][j], ep, b, co, Cout);
@@ -269,19 +276,26 @@ int conv1d_simt_launch(void* dst, int64_t dsb, const void* src, const void* src2
     BVG_CHECK_ARG(T > dil * (K - 1) / 2, "conv1d: reflect padding needs T > pad (T=%lld pad=%d)", (long long)T,
                   dil * (K - 1) / 2);
   if (B == 0 || T == 0) return BVG_OK;
-  BVG_CHECK_ARG(B <= 65535 && (Cout + kTC - 1) / kTC <= 65535, "conv1d: batch/channel grid too large");
-  dim3 grid((unsigned)((T + kTT - 1) / kTT), (unsigned)((Cout + kTC - 1) / kTC), (unsigned)B);
+  // small problems (few output channels, or too few 128 x 128 tiles to fill the GPU) take 64 x 64 tiles
+  const int64_t tiles128 = ((T + 127) / 128) * ((Cout + 127) / 128) * B;
+  const bool small = in_dtype == BVG_F32 && out_dtype == BVG_F32 && (Cout <= 64 || tiles128 < 148);
+  const int tile = small ? 64 : 128;
+  BVG_CHECK_ARG(B <= 65535 && (Cout + tile - 1) / tile <= 65535, "conv1d: batch/channel grid too large");
+  dim3 grid((unsigned)((T + tile - 1) / tile), (unsigned)((Cout + tile - 1) / tile), (unsigned)B);
   EpiDev e = to_dev(ep);
   ProfScope prof(st, (T >= 64 && !ep.prof_other) ? KC_CONV : KC_OTHER);
-  if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
-    conv1d_simt_kernel<float, float><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
-                                                           sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);
+  if (small)
+    conv1d_simt_kernel<float, float, 4><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
+                                                              sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);
+  else if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
+    conv1d_simt_kernel<float, float, 8><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
+                                                              sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);
   else if (in_dtype == BVG_BF16 && out_dtype == BVG_BF16)
-    conv1d_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+    conv1d_simt_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<grid, 256, 0, st>>>(
         (__nv_bfloat16*)dst, dsb, (const __nv_bfloat16*)src, (const __nv_bfloat16*)src2, sb, sc, st_, weight_kic, e,
         Cin, Cout, T, K, dil, pad_mode);
   else if (in_dtype == BVG_F32 && out_dtype == BVG_BF16)
-    conv1d_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, dsb, (const float*)src,
+    conv1d_simt_kernel<float, __nv_bfloat16, 8><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, dsb, (const float*)src,
                                                                    (const float*)src2, sb, sc, st_, weight_kic, e,
                                                                    Cin, Cout, T, K, dil, pad_mode);
   else {
