@@ -224,18 +224,27 @@ int launch_typed(void* dst, const void* src, const float* a, const float* b, int
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPRows = 16;
 constexpr int kPW = 512;
-constexpr int kPPitch = kPW + 2 * kHalo;       // 528 elements
-
-template <typename T> __device__ __forceinline__ float ld_f(const T* p, int i) { return to_f<T>(p[i]); }
+constexpr int kPPitch = kPW + 2 * kHalo;       // 528 staged elements per row
+// Row pitches in shared memory are == 16 (mod 128) bytes and the 8 lanes of a quarter-warp own 8 different rows
+// (same 16-sample segment): their 128-bit loads / stores then fall into 8 different 16-byte bank groups.  (With lanes
+// spread along a row instead, every segment starts at a multiple of 64 bytes and the accesses are 4-way conflicted.)
+template <typename T> struct PairSmem {
+  static constexpr int kInPitch = (kPPitch * (int)sizeof(T) + 127) / 128 * 128 + 16;   // bytes
+  static constexpr int kOutPitch = kPW * (int)sizeof(T) + 16;                           // bytes
+  static constexpr int kBytes = kPRows * (kInPitch + kOutPitch) + 16;
+};
 
 template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __restrict__ alpha_log,
                   const float* __restrict__ beta_log, int64_t rows, int C, int64_t Tlen, int col_tiles) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  T (*tile)[kPPitch] = reinterpret_cast<T (*)[kPPitch]>(smem_raw);
-  T (*otile)[kPW] = reinterpret_cast<T (*)[kPW]>(smem_raw + sizeof(T) * kPRows * kPPitch);     // results, row-major
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(T) * kPRows * (kPPitch + kPW));
+  constexpr int IP = PairSmem<T>::kInPitch, OP = PairSmem<T>::kOutPitch;
+  uint8_t* tile_b = smem_raw;                                     // [kPRows] rows of IP bytes
+  uint8_t* otile_b = smem_raw + kPRows * IP;                      // [kPRows] rows of OP bytes (results, row-major)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kPRows * (IP + OP));
+  auto tile = [&](int rr) { return reinterpret_cast<T*>(tile_b + rr * IP); };
+  auto otile = [&](int rr) { return reinterpret_cast<T*>(otile_b + rr * OP); };
 
   const int tid = threadIdx.x;
   const int64_t blk = blockIdx.x;
@@ -243,13 +252,15 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
   const int64_t t0 = (blk % col_tiles) * (int64_t)kPW;
   const int nrows = (int)min((int64_t)kPRows, rows - row0);
 
-  // thread = row pair (tid >> 5) x 16-sample group (tid & 31)
-  const int r = (tid >> 5) * 2;
-  const int c0 = (tid & 31) * 16;
+  // thread = rows (p, p + 8) x 16-sample group: p = tid & 7, group = tid >> 3  (a tile with <= 8 rows pairs (p, p + 4)
+  // on half of the threads instead of falling back to the scalar single-row path)
+  const int half = nrows > 8 ? 8 : 4;
+  const int r = tid & 7, r2 = r + half;
+  const int c0 = (tid >> 3) * 16;
   const int64_t tg = t0 + c0;
   float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;     // snake parameters first: the loads overlap the TMA wait
   if (r < nrows) snake_params<false>(alpha_log[(int)((row0 + r) % C)], beta_log[(int)((row0 + r) % C)], a0, b0);
-  if (r + 1 < nrows) snake_params<false>(alpha_log[(int)((row0 + r + 1) % C)], beta_log[(int)((row0 + r + 1) % C)], a1, b1);
+  if (r2 < nrows) snake_params<false>(alpha_log[(int)((row0 + r2) % C)], beta_log[(int)((row0 + r2) % C)], a1, b1);
 
   if (ALIGNED) {
     const int64_t lo = max(t0 - kHalo, (int64_t)0);
@@ -263,7 +274,7 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
     if (tid == 0) {
       mbar_expect_tx(bar, bytes * nrows);
       for (int rr = 0; rr < nrows; ++rr)
-        bulk_g2s(&tile[rr][lo - (t0 - kHalo)], src + (row0 + rr) * Tlen + lo, bytes, bar);
+        bulk_g2s(tile(rr) + (lo - (t0 - kHalo)), src + (row0 + rr) * Tlen + lo, bytes, bar);
     }
     mbar_wait(bar, 0);
   } else {
@@ -272,20 +283,20 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
       const int64_t t = t0 - kHalo + c;
       T v = from_f<T>(0.f);
       if (rr < nrows && t >= 0 && t < Tlen) v = src[(row0 + rr) * Tlen + t];
-      tile[rr][c] = v;
+      tile(rr)[c] = v;
     }
     __syncthreads();
   }
   constexpr int V = 16;
-  if (r < nrows && tg < Tlen) {
-  const int nr = min(2, nrows - r);
+  if (r < half && r < nrows && tg < Tlen) {
+  const int nr = r2 < nrows ? 2 : 1;
   const bool interior = (tg - 5 >= 0) && (tg + V + 4 <= Tlen - 1) && nr == 2;
   if (interior) {
-    // window position j <-> tile[row][c0 + j] (time tg - 8 + j); rows are fetched 16 bytes at a time as the stencil
+    // window position j <-> tile(row)[c0 + j] (time tg - 8 + j); rows are fetched 16 bytes at a time as the stencil
     // walks down the window (everything is unrolled, so `j` is a compile-time constant in each call)
     constexpr int VE = 16 / sizeof(T);                     // elements per 128-bit shared-memory load
-    const uint4* va = reinterpret_cast<const uint4*>(&tile[r][c0]);
-    const uint4* vb = reinterpret_cast<const uint4*>(&tile[r + 1][c0]);
+    const uint4* va = reinterpret_cast<const uint4*>(tile(r) + c0);
+    const uint4* vb = reinterpret_cast<const uint4*>(tile(r2) + c0);
     uint4 ca = va[0], cb = vb[0];
     float ya[V], yb[V];
     act1d_window2<V>(
@@ -309,18 +320,19 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
         },
         [&](int q, float va_, float vb_) { ya[q] = va_; yb[q] = vb_; },
         pk2(a0, a1), pk2(b0, b1));
-    store8_vec<T>(&otile[r][c0], *reinterpret_cast<float(*)[8]>(&ya[0]));
-    store8_vec<T>(&otile[r][c0 + 8], *reinterpret_cast<float(*)[8]>(&ya[8]));
-    store8_vec<T>(&otile[r + 1][c0], *reinterpret_cast<float(*)[8]>(&yb[0]));
-    store8_vec<T>(&otile[r + 1][c0 + 8], *reinterpret_cast<float(*)[8]>(&yb[8]));
+    store8_vec<T>(otile(r) + c0, *reinterpret_cast<float(*)[8]>(&ya[0]));
+    store8_vec<T>(otile(r) + c0 + 8, *reinterpret_cast<float(*)[8]>(&ya[8]));
+    store8_vec<T>(otile(r2) + c0, *reinterpret_cast<float(*)[8]>(&yb[0]));
+    store8_vec<T>(otile(r2) + c0 + 8, *reinterpret_cast<float(*)[8]>(&yb[8]));
   } else {
     for (int h = 0; h < nr; ++h) {          // sequence edges / odd last row: scalar stencil with replicate padding
+      const int rr = h ? r2 : r;
       float xw[V + 16], y[V];
 #pragma unroll
-      for (int j = 0; j < V + 16; ++j) xw[j] = to_f<T>(tile[r + h][c0 + j]);
+      for (int j = 0; j < V + 16; ++j) xw[j] = to_f<T>(tile(rr)[c0 + j]);
       act1d_window<V, false>(xw, y, h ? a1 : a0, h ? b1 : b0, tg, Tlen);
 #pragma unroll
-      for (int q = 0; q < V; ++q) otile[r + h][c0 + q] = from_f<T>(y[q]);
+      for (int q = 0; q < V; ++q) otile(rr)[c0 + q] = from_f<T>(y[q]);
     }
   }
   }
@@ -331,7 +343,7 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
     __syncthreads();
     if (tid < nrows) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (row0 + tid) * Tlen + t0),
-                   "r"(smem_u32(&otile[tid][0])), "r"((uint32_t)(ncols * sizeof(T))) : "memory");
+                   "r"(smem_u32(otile(tid))), "r"((uint32_t)(ncols * sizeof(T))) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -339,7 +351,7 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
     __syncthreads();
     for (int idx = tid; idx < nrows * kPW; idx += 256) {
       const int rr = idx / kPW, c = idx % kPW;
-      if (c < ncols) dst[(row0 + rr) * Tlen + t0 + c] = otile[rr][c];
+      if (c < ncols) dst[(row0 + rr) * Tlen + t0 + c] = otile(rr)[c];
     }
   }
 }
@@ -353,7 +365,7 @@ int launch_pair(void* dst, const void* src, const float* a, const float* b, int6
   BVG_CHECK_ARG(nblk < (1ll << 31), "act1d: problem too large (%lld CTAs)", (long long)nblk);
   const bool aligned = (Tlen % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-  const size_t smem = sizeof(T) * kPRows * (kPPitch + kPW) + 16;
+  const size_t smem = PairSmem<T>::kBytes;
   static bool attr = false;
   if (!attr) {
     BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
