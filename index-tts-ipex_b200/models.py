@@ -445,3 +445,42 @@ class BigVGAN(nn.Module):
             hi = min(halo_frames, T0 - e)
             outs.append(self.decode(x[:, s - lo:e + hi], spk=spk, pcm16=pcm16, halo=(lo, hi)))
         return torch.cat(outs, dim=-1)
+
+    @torch.no_grad()
+    def decode_ragged(self, latents, mel_refs, pcm16=False):
+        """Batched vocoding of utterances of DIFFERENT lengths (what `infer_fast` works around by concatenating two
+        sentences in time at B = 1, `indextts/infer.py:480-503`).  `latents` is a sequence of `[T0_i, gpt_dim]`
+        tensors, `mel_refs` one `[Tm, num_mels]` reference for all of them or a sequence with one per utterance.
+        The generator has no length masks and its edge handling (zero-padded convs, replicate-padded anti-alias
+        filters) depends on where each utterance ends, so padding to a common length would change the last ~35
+        frames; instead utterances of equal length are batched together and every waveform equals the one a
+        single-utterance call returns.  Speaker embeddings are computed once per distinct reference.
+        Returns a list of `[1, T0_i * 1024]` waveforms (or `[T0_i * 1024]` int16 with pcm16) in input order."""
+        lat = [t if t.dim() == 2 else t.squeeze(0) for t in latents]
+        n = len(lat)
+        if n == 0:
+            return []
+        dev = lat[0].device
+        shared = torch.is_tensor(mel_refs)
+        mels = [mel_refs] * n if shared else list(mel_refs)
+        if len(mels) != n:
+            raise RuntimeError(f"decode_ragged: {n} latents but {len(mels)} reference mels")
+        # one speaker-encoder pass per distinct reference tensor (the web UI reuses one voice for many sentences)
+        spk_of = {}
+        for m in mels:
+            key = (m.data_ptr(), tuple(m.shape))
+            if key not in spk_of:
+                mm = m if m.dim() == 3 else m.unsqueeze(0)
+                spk_of[key] = self.speaker_embed(mm.to(dev))
+        out = [None] * n
+        groups = {}
+        for i, t in enumerate(lat):
+            groups.setdefault(int(t.shape[0]), []).append(i)
+        for T0, idx in groups.items():
+            x = torch.stack([lat[i] for i in idx], 0)
+            spk = torch.cat([spk_of[(mels[i].data_ptr(), tuple(mels[i].shape))] for i in idx], 0)
+            y = self.decode(x, spk=spk, pcm16=pcm16)
+            for j, i in enumerate(idx):
+                out[i] = y[j]
+        return out
+

@@ -321,3 +321,31 @@ def test_cuda_graph_decode_matches_eager(P):
         finally:
             m.precision = None
         assert torch.equal(a, eager) and torch.equal(b, eager2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_batch_equals_single_utterance_decodes(P, precision):
+    """utterances of different lengths in one call; every waveform must equal what a
+    single-utterance call returns (no padding to a common length: the edge handling depends on where each
+    utterance ends), in input order, with one speaker-encoder pass per distinct reference."""
+    m, sd, h = _model(P, "small", 5, "wild")
+    m.precision = precision
+    try:
+        lens = [9, 14, 9, 3, 14, 21]
+        gen = torch.Generator().manual_seed(3)
+        lats = [torch.randn(t, h.gpt_dim, generator=gen).cuda() for t in lens]
+        mel_a = (torch.randn(40, h.num_mels, generator=gen) * 2.5 - 0.3).cuda()
+        mel_b = (torch.randn(33, h.num_mels, generator=gen) * 2.5 - 0.3).cuda()
+        mels = [mel_a, mel_b, mel_a, mel_a, mel_b, mel_b]
+        outs = m.decode_ragged(lats, mels)
+        assert [tuple(o.shape) for o in outs] == [(1, t * m.total_upsample) for t in lens]
+        for x, mel, y in zip(lats, mels, outs):
+            one = m.decode(x[None], spk=m.speaker_embed(mel[None]))[0]
+            assert torch.equal(one, y)
+        shared = m.decode_ragged(lats[:3], mel_a, pcm16=True)
+        assert shared[1].dtype == torch.int16 and shared[1].shape == (lens[1] * m.total_upsample,)
+        with pytest.raises(RuntimeError):
+            m.decode_ragged(lats, mels[:2])
+        assert m.decode_ragged([], mels) == []
+    finally:
+        m.precision = None
