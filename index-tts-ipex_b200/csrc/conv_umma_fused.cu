@@ -271,13 +271,15 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         uint32_t xph = 0, wph = 0, aph = 0;
         long long dbg_wx = 0, dbg_wt = 0, dbg_ww = 0;
         const long long dbg_start = P.dbg ? clock64() : 0;
+        unsigned long long dbg_ns0 = 0;
+        if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
         for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
-          { DBG_T0(); mbar_wait(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }
+          { DBG_T0(); mbar_wait_backoff(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t dbase = tmem_base + (uint32_t)(as * acc_cols);
           for (int blk = 0; blk < nblk; ++blk) {
             const int nk = min(kFBlk / 8, (P.Cin_p >> 3) - blk * (kFBlk / 8)) >> 1;   // 16-channel steps (1..3)
-            { DBG_T0(); mbar_wait(&full_x[xs], xph); DBG_ADD(dbg_wx); }   // the stencil warps filled this A stage
+            { DBG_T0(); mbar_wait_backoff(&full_x[xs], xph); DBG_ADD(dbg_wx); }   // the stencil warps filled this A stage
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
             for (int tp = 0; tp < P.ntaps; ++tp) {
@@ -310,9 +312,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             if (++xs == nast) { xs = 0; xph ^= 1; }
           }
           umma_commit_elect(&tmem_full[as]);
-          if (++as == 2) { as = 0; aph ^= 1; }
+          if (++as == P.acc_stages) { as = 0; aph ^= 1; }
         }
-        if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 16; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; d[8] = dbg_ww; }
+        if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 16; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; d[8] = dbg_ww;
+          unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1)); d[9] = (long long)(ns1 - dbg_ns0); }
       }
     }
   } else if (warp >= kFEpiWarp0) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == P.acc_stages) { as = 0; aph ^= 1; }
       if (P.zero_pads) {
         // rows [-PAD, 0) by the first tile, [Tout, Tout+PAD) by the last: keeps the c8t zero halo intact
         const int et = threadIdx.x - kFEpiWarp0 * 32;
@@ -486,7 +489,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   int n_nblk = 1;
   P.NPH = 1;
   umma_choose_nb(L.Cout, 1, &P.NB, &n_nblk);
-  if (n_nblk != 1 || P.NB > 128 || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
+  if (n_nblk != 1 || P.NB > env_int("BVG_FUSE_MAX_NB", 128) || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
   P.ntaps = L.K;
   BVG_CHECK_ARG(L.K <= 16, "conv_umma_fused: at most 16 taps");
   // Wide-and-long layers (C = 96, k = 11) are bound by the number of narrow tcgen05.mma instructions (~100-150 cycles
@@ -521,14 +524,17 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   int xr = std::min(512, std::max(1, kFLanes / nwords) * kFV);
   if (const int e = env_int("BVG_FUSE_XR", 0)) xr = e / kFV * kFV;
   auto nacc_of = [&](int rows) { return (rows - halo + 127) / 128; };
-  while (xr > halo + kFV && 2 * nacc_of(xr) * P.NB > 512) xr -= kFV;
-  if (xr < halo + kFV || 2 * nacc_of(xr) * P.NB > 512) return BVG_ERR_STATE;
+  // two accumulator stages (the epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 TMEM columns
+  // at full stencil occupancy; wide layers (C = 192) keep the full tile and run with one stage instead
+  if (2 * nacc_of(xr) * P.NB > 512 && nacc_of(xr) * P.NB <= 512 && P.NB > 128) P.acc_stages = 1;
+  while (xr > halo + kFV && P.acc_stages * nacc_of(xr) * P.NB > 512) xr -= kFV;
+  if (xr < halo + kFV || P.acc_stages * nacc_of(xr) * P.NB > 512) return BVG_ERR_STATE;
   P.XR = xr;
   P.rows_out = xr - halo;
   P.MT = nacc_of(xr);
   P.tiles_per_batch = (y.T + P.rows_out - 1) / P.rows_out;
   int pw = 32;
-  while (pw < 2 * P.MT * P.NB) pw <<= 1;
+  while (pw < P.acc_stages * P.MT * P.NB) pw <<= 1;
   P.tmem_cols = pw;
   P.n_issuers = P.MT >= 2 ? 2 : 1;
   // shared memory: raw ring + A ring + weights (resident when they fit next to 2+2 stages, else a ring of slots)
@@ -544,7 +550,9 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
     P.w_stages = wslots;
   } else {
     P.w_resident = 0;
-    P.w_stages = (int)std::min<size_t>({(size_t)kFMaxW, (budget - used) / wsb, (size_t)std::max(2, std::min(wslots, 8))});
+    // (with one accumulator stage the A ring, not the weight ring, is what keeps the stencil running: cap at 4 slots)
+    P.w_stages = (int)std::min<size_t>({(size_t)kFMaxW, (budget - used) / wsb,
+                                        (size_t)std::max(2, std::min(wslots, P.acc_stages == 1 ? 4 : 8))});
   }
   used += P.w_stages * wsb;
   // leftover: deepen the A ring first (lets the stencil run ahead of the MMAs), then the raw ring
@@ -553,8 +561,9 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   P.a_stages = 2; P.x_stages = 2;
   for (bool grew = true; grew;) {
     grew = false;
+    if (P.acc_stages == 1 && P.a_stages < max_a && used + xsb <= budget) { ++P.a_stages; used += xsb; grew = true; }
     if (P.x_stages < max_raw && used + rsb <= budget) { ++P.x_stages; used += rsb; grew = true; }
-    if (P.a_stages < max_a && used + xsb <= budget) { ++P.a_stages; used += xsb; grew = true; }
+    if (P.acc_stages == 2 && P.a_stages < max_a && used + xsb <= budget) { ++P.a_stages; used += xsb; grew = true; }
   }
   const size_t smem = used + fused_fixed_smem(P.NB, P.Cin_p);
   static bool attr_set = false;
