@@ -50,9 +50,9 @@ def peaks():
 FUSED_MAX_C = 128      # AMPBlock1 act->conv pairs with C <= 128 run as one fused kernel (conv_umma_fused.cu)
 # dram__bytes_read.sum + dram__bytes_write.sum per fused launch, averaged over the 54 fused launches of one benchmark
 # step (ncu capture of tools/prof_decode.py; see the named file)
-FUSED_TRAFFIC_PER_LAUNCH = 957.9e6
-FUSED_TRAFFIC_NOTE = ("profiles/r01_fused_dram_v6.csv: ncu dram__bytes_read.sum + dram__bytes_write.sum of the 54 fused "
-                      "launches of one step (B = 32 x 10 s): 51.73 GB in total = 957.9 MB per launch")
+FUSED_TRAFFIC_PER_LAUNCH = 959.7e6
+FUSED_TRAFFIC_NOTE = ("profiles/r01_fused_dram_v7.csv: ncu dram__bytes_read.sum + dram__bytes_write.sum of the 54 fused "
+                      "launches of one step (B = 32 x 10 s): 51.82 GB in total = 959.7 MB per launch")
 
 
 def algorithmic_work(h, B, T0_, es=2, fused=True):
