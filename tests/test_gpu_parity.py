@@ -349,3 +349,23 @@ def test_ragged_batch_equals_single_utterance_decodes(P, precision):
         assert m.decode_ragged([], mels) == []
     finally:
         m.precision = None
+
+
+@pytest.mark.parametrize("T0", [1, 2, 3, 5, 17])
+def test_bf16_path_tiny_lengths_full_config(P, T0):
+    """Very short utterances on the full IndexTTS-1.5 config: every stage is shorter than one tile of the fused
+    Activation1d->conv kernel at T0 = 1 (stage 3 has 256 rows), so this exercises its clipping of raw rows, the
+    replicate-padded stencil edges and the dropped accumulator rows.  bf16 vs the fp32 path of the same library
+    (itself pinned to the reference goldens), and fused vs two-kernel path through the environment switch."""
+    m, sd, h = _model(P, "indextts15", 0, "tame")
+    latent, mel = O.synthetic_inputs(h, 2, T0, 281, seed=40 + T0)
+    m.precision = "fp32"
+    try:
+        ref = m.decode(latent.cuda(), mel_ref=mel.cuda())
+        m.precision = "bf16"
+        y = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    finally:
+        m.precision = None
+    assert y.shape == (2, 1, T0 * 1024) and torch.isfinite(y).all()
+    snr = O.snr_db(ref.cpu(), y.cpu())
+    assert snr >= BF16_SNR_GATE, snr
