@@ -21,7 +21,6 @@ constexpr int kTT = 128;     // time steps per CTA
 constexpr int kTC = 128;     // output channels per CTA
 constexpr int kCK = 16;      // input channels per chunk
 constexpr int kMaxHalo = 64; // (K-1)*dil <= 64  (generator max: (11-1)*5 = 50)
-constexpr int kXW = kTT + kMaxHalo;
 
 struct EpiDev {
   const float* bias;
@@ -58,7 +57,8 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
                    int64_t Cin, int64_t Cout, int64_t T, int K, int dil, int pad_mode) {
   constexpr int kTT = 16 * NT, kTC = 16 * NT, kXW = kTT + kMaxHalo;
   __shared__ float xs[kCK][kXW];
-  __shared__ __align__(16) float ws[kCK][kTC];
+  // two weight slabs: the [16 x TC] slab of the next tap streams in with cp.async while this tap's FMAs run
+  __shared__ __align__(16) float ws[2][kCK][kTC];
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -77,43 +77,67 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
   const TI* sbase = src + b * sb;
   const TI* sbase2 = src2 ? src2 + b * sb : nullptr;
 
-  for (int64_t ci0 = 0; ci0 < Cin; ci0 += kCK) {
-    __syncthreads();   // previous chunk's readers are done with xs/ws
-    for (int idx = tid; idx < kCK * xw; idx += 256) {
-      const int ci = idx / xw, p = idx - ci * xw;
-      int64_t t = t0 - pad + p;
-      float v = 0.f;
-      if (ci0 + ci < Cin) {
-        if (pad_mode == 1) {  // reflect
-          if (t < 0) t = -t;
-          if (t >= T) t = 2 * (T - 1) - t;
-          if (t < 0) t = 0;   // (only reachable when T <= pad; guarded on the host)
-        }
-        if (t >= 0 && t < T) {
-          const int64_t off = (ci0 + ci) * sc + t * st_;
-          v = to_f<TI>(sbase[off]);
-          if (sbase2) v += to_f<TI>(sbase2[off]);
-        }
+  // weight slab of iteration (ci0, k) -> ws[buf]: 16-byte cp.async per thread, zero-filled outside [Cin) x [Cout)
+  // (Cout % 4 == 0 and a 16-byte aligned weight pointer: whole 4-float groups are in or out); scalar loads otherwise
+  const bool vec_w = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  auto issue_w = [&](int64_t ci0, int k, int buf) {
+    const float* wk = w + ((int64_t)k * Cin + ci0) * Cout + co0;
+    if (vec_w) {
+      for (int idx = tid; idx < kCK * (kTC / 4); idx += 256) {
+        const int ci = idx / (kTC / 4), c = (idx % (kTC / 4)) * 4;
+        const bool in = (ci0 + ci < Cin) && (co0 + c < Cout);
+        const float* srcp = in ? wk + (int64_t)ci * Cout + c : w;
+        const uint32_t dsts = static_cast<uint32_t>(__cvta_generic_to_shared(&ws[buf][ci][c]));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dsts), "l"(srcp), "r"(in ? 16 : 0) : "memory");
       }
-      xs[ci][p] = v;
-    }
-    for (int k = 0; k < K; ++k) {
-      if (k) __syncthreads();
-      const float* wk = w + ((int64_t)k * Cin + ci0) * Cout + co0;
+    } else {
       for (int idx = tid; idx < kCK * kTC; idx += 256) {
         const int ci = idx / kTC, c = idx % kTC;
         float v = 0.f;
         if (ci0 + ci < Cin && co0 + c < Cout) v = wk[(int64_t)ci * Cout + c];
-        ws[ci][c] = v;
+        ws[buf][ci][c] = v;
       }
-      __syncthreads();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  issue_w(0, 0, 0);
+  for (int64_t ci0 = 0; ci0 < Cin; ci0 += kCK) {
+    for (int k = 0; k < K; ++k) {
+      __syncthreads();   // everyone is done with the previous iteration: xs (at k == 0) and ws[buf ^ 1] may be overwritten
+      const bool last = (k + 1 == K) && (ci0 + kCK >= Cin);
+      if (!last) issue_w(k + 1 < K ? ci0 : ci0 + kCK, k + 1 < K ? k + 1 : 0, buf ^ 1);
+      if (k == 0) {
+        for (int idx = tid; idx < kCK * xw; idx += 256) {
+          const int ci = idx / xw, p = idx - ci * xw;
+          int64_t t = t0 - pad + p;
+          float v = 0.f;
+          if (ci0 + ci < Cin) {
+            if (pad_mode == 1) {  // reflect
+              if (t < 0) t = -t;
+              if (t >= T) t = 2 * (T - 1) - t;
+              if (t < 0) t = 0;   // (only reachable when T <= pad; guarded on the host)
+            }
+            if (t >= 0 && t < T) {
+              const int64_t off = (ci0 + ci) * sc + t * st_;
+              v = to_f<TI>(sbase[off]);
+              if (sbase2) v += to_f<TI>(sbase2[off]);
+            }
+          }
+          xs[ci][p] = v;
+        }
+      }
+      if (last) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();   // this iteration's slab (and the x tile) are visible to all threads
       const int shift = k * dil + tx;
 #pragma unroll 4
       for (int ci = 0; ci < kCK; ++ci) {
         float wv[NT];
 #pragma unroll
         for (int i = 0; i < NT; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&ws[ci][ty * NT + i]);
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[buf][ci][ty * NT + i]);
           wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
         }
         float xv[NT];
@@ -124,6 +148,7 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
 #pragma unroll
           for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
       }
+      buf ^= 1;
     }
   }
 
