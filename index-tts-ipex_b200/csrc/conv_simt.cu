@@ -267,6 +267,105 @@ convtr1d_simt_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const flo
   }
 }
 
+// Same op with all lanes busy: a thread owns 8/U coarse positions q = tx + 16*jq and ALL U output phases of each
+// (t = t0 + U*q + ph).  Tap k only feeds phase ph = (k - p) mod U, so with the phase loop outside (compile-time
+// accumulator index) every tap is a plain strided-free FMA pass for the whole warp, where the kernel above keeps
+// 1/U of the lanes busy per tap.  U = stride in {2, 4} (the generator's), 128 x 128 tile, same weight layout.
+template <typename TT, int U>
+__global__ void __launch_bounds__(256)
+convtr1d_simt_phase_kernel(TT* __restrict__ dst, const TT* __restrict__ src, const float* __restrict__ w, EpiDev ep,
+                           int64_t Cin, int64_t Cout, int64_t Tin, int K) {
+  constexpr int kXI = 96;   // input steps staged: 128/U + K/U + 2 <= 96
+  constexpr int NT = 8, NQ = NT / U;
+  __shared__ float xs[kCK][kXI];
+  __shared__ __align__(16) float ws[kCK][kTC];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t Tout = Tin * U;
+  const int64_t t0 = (int64_t)blockIdx.x * kTT;
+  const int64_t co0 = (int64_t)blockIdx.y * kTC;
+  const int64_t b = blockIdx.z;
+  const int p = (K - U) / 2;
+  // input index range touched by this tile
+  const int64_t n_lo = t0 + p - (K - 1);
+  const int64_t i_lo = (n_lo >= 0) ? n_lo / U : -((-n_lo + U - 1) / U);
+  const int64_t i_hi = (t0 + kTT - 1 + p) / U;
+  const int ni = (int)(i_hi - i_lo + 1);
+
+  float acc[NT][NT];        // acc[i][jq * U + ph]
+#pragma unroll
+  for (int i = 0; i < NT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+
+  const TT* sbase = src + b * Cin * Tin;
+  for (int64_t ci0 = 0; ci0 < Cin; ci0 += kCK) {
+    __syncthreads();
+    for (int idx = tid; idx < kCK * ni; idx += 256) {
+      const int ci = idx / ni, q = idx - ci * ni;
+      const int64_t i = i_lo + q;
+      float v = 0.f;
+      if (ci0 + ci < Cin && i >= 0 && i < Tin) v = to_f<TT>(sbase[(ci0 + ci) * Tin + i]);
+      xs[ci][q] = v;
+    }
+    bool first = true;
+#pragma unroll
+    for (int ph = 0; ph < U; ++ph) {
+      for (int k = (ph + p) % U; k < K; k += U) {
+        if (!first) __syncthreads();
+        first = false;
+        const float* wk = w + ((int64_t)k * Cin + ci0) * Cout + co0;
+        for (int idx = tid; idx < kCK * kTC; idx += 256) {
+          const int ci = idx / kTC, c = idx % kTC;
+          float v = 0.f;
+          if (ci0 + ci < Cin && co0 + c < Cout) v = wk[(int64_t)ci * Cout + c];
+          ws[ci][c] = v;
+        }
+        __syncthreads();
+        // input index of coarse position q for this tap: i = t0/U + q + (ph + p - k)/U  (exact division)
+        const int64_t ib = t0 / U + (ph + p - k) / U;
+        int qi[NQ];
+        bool ok[NQ];
+#pragma unroll
+        for (int jq = 0; jq < NQ; ++jq) {
+          const int64_t i = ib + tx + 16 * jq;
+          ok[jq] = (i >= 0) && (i < Tin);
+          qi[jq] = ok[jq] ? (int)(i - i_lo) : 0;
+        }
+#pragma unroll 4
+        for (int ci = 0; ci < kCK; ++ci) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[ci][ty * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[ci][ty * 8 + 4]);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float xv[NQ];
+#pragma unroll
+          for (int jq = 0; jq < NQ; ++jq) xv[jq] = ok[jq] ? xs[ci][qi[jq]] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int jq = 0; jq < NQ; ++jq) acc[i][jq * U + ph] = fmaf(wv[i], xv[jq], acc[i][jq * U + ph]);
+        }
+      }
+    }
+  }
+  TT* dbase = dst + b * Cout * Tout;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int64_t co = co0 + ty * NT + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int jq = 0; jq < NQ; ++jq)
+#pragma unroll
+      for (int ph = 0; ph < U; ++ph) {
+        const int64_t t = t0 + (int64_t)U * (tx + 16 * jq) + ph;
+        if (t >= Tout) continue;
+        float v = epilogue_apply(acc[i][jq * U + ph], ep, b, co, Cout);
+        dbase[co * Tout + t] = from_f<TT>(v * ep.scale);
+      }
+  }
+}
+
 __global__ void repack_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t Cout, int64_t Cin,
                               int K, int transposed) {
   // dst[k][ci][co]
@@ -344,7 +443,17 @@ int convtr1d_simt_launch(void* dst, const void* src, const float* weight_kic, co
   dim3 grid((unsigned)((Tout + kTT - 1) / kTT), (unsigned)((Cout + kTC - 1) / kTC), (unsigned)B);
   EpiDev e = to_dev(ep);
   ProfScope prof(st, KC_CONVTR);
-  if (dtype == BVG_F32)
+  if (dtype == BVG_F32 && stride == 4)
+    convtr1d_simt_phase_kernel<float, 4><<<grid, 256, 0, st>>>((float*)dst, (const float*)src, weight_kic, e, Cin, Cout, Tin, K);
+  else if (dtype == BVG_F32 && stride == 2)
+    convtr1d_simt_phase_kernel<float, 2><<<grid, 256, 0, st>>>((float*)dst, (const float*)src, weight_kic, e, Cin, Cout, Tin, K);
+  else if (dtype == BVG_BF16 && stride == 4)
+    convtr1d_simt_phase_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src,
+                                                                       weight_kic, e, Cin, Cout, Tin, K);
+  else if (dtype == BVG_BF16 && stride == 2)
+    convtr1d_simt_phase_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src,
+                                                                       weight_kic, e, Cin, Cout, Tin, K);
+  else if (dtype == BVG_F32)
     convtr1d_simt_kernel<float><<<grid, 256, 0, st>>>((float*)dst, (const float*)src, weight_kic, e, Cin, Cout, Tin, K,
                                                       stride);
   else if (dtype == BVG_BF16)
