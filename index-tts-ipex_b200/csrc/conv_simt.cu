@@ -48,14 +48,16 @@ __device__ __forceinline__ float final_act(float v, int act) {
   return v;
 }
 
-// NT = accumulators per thread and dimension: 8 -> the 128 x 128 tile above, 4 -> a 64 x 64 tile for the small layers
-// of the speaker encoder (Res2Net 64 -> 64 convs over 281 frames: four times as many CTAs, a quarter of the serial work)
-template <typename TI, typename TO, int NT>
+// NI x NJ accumulators per thread (output channels x time steps): tile = 16*NI channels x 16*NJ time steps.
+// 8 x 8 is the 128 x 128 tile above; 4 x 4 a 64 x 64 tile for the small layers of the speaker encoder (Res2Net
+// 64 -> 64 convs over 281 frames: four times as many CTAs, a quarter of the serial work); 6 / 3 / 2 x 8 fit the
+// narrow generator stages (C = 96 / 48 / 24) without computing padding channels.
+template <typename TI, typename TO, int NI, int NJ>
 __global__ void __launch_bounds__(256)
 conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src, const TI* __restrict__ src2,
                    int64_t sb, int64_t sc, int64_t st_, const float* __restrict__ w, EpiDev ep,
                    int64_t Cin, int64_t Cout, int64_t T, int K, int dil, int pad_mode) {
-  constexpr int kTT = 16 * NT, kTC = 16 * NT, kXW = kTT + kMaxHalo;
+  constexpr int kTT = 16 * NJ, kTC = 16 * NI, kXW = kTT + kMaxHalo;
   __shared__ float xs[kCK][kXW];
   // two weight slabs: the [16 x TC] slab of the next tap streams in with cp.async while this tap's FMAs run
   __shared__ __align__(16) float ws[2][kCK][kTC];
@@ -68,11 +70,11 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
   const int pad = dil * (K - 1) / 2;
   const int xw = kTT + dil * (K - 1);
 
-  float acc[NT][NT];
+  float acc[NI][NJ];
 #pragma unroll
-  for (int i = 0; i < NT; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 
   const TI* sbase = src + b * sb;
   const TI* sbase2 = src2 ? src2 + b * sb : nullptr;
@@ -134,19 +136,30 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
       const int shift = k * dil + tx;
 #pragma unroll 4
       for (int ci = 0; ci < kCK; ++ci) {
-        float wv[NT];
+        float wv[NI];
+        if (NI % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < NT; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&ws[buf][ci][ty * NT + i]);
-          wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+          for (int i = 0; i + 3 < NI; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&ws[buf][ci][ty * NI + i]);
+            wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+          }
+        } else if (NI % 2 == 0) {
+#pragma unroll
+          for (int i = 0; i + 1 < NI; i += 2) {
+            const float2 w2 = *reinterpret_cast<const float2*>(&ws[buf][ci][ty * NI + i]);
+            wv[i] = w2.x; wv[i + 1] = w2.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) wv[i] = ws[buf][ci][ty * NI + i];
         }
-        float xv[NT];
+        float xv[NJ];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) xv[j] = xs[ci][shift + 16 * j];
+        for (int j = 0; j < NJ; ++j) xv[j] = xs[ci][shift + 16 * j];
 #pragma unroll
-        for (int i = 0; i < NT; ++i)
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
-          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+          for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
       }
       buf ^= 1;
     }
@@ -156,11 +169,11 @@ conv1d_simt_kernel(TO* __restrict__ dst, int64_t dsb, const TI* __restrict__ src
   const TO* r1 = ep.res1 ? static_cast<const TO*>(ep.res1) + b * dsb : nullptr;
   const TO* r2 = ep.res2 ? static_cast<const TO*>(ep.res2) + b * dsb : nullptr;
 #pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    const int64_t co = co0 + ty * NT + i;
+  for (int i = 0; i < NI; ++i) {
+    const int64_t co = co0 + ty * NI + i;
     if (co >= Cout) continue;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int64_t t = t0 + tx + 16 * j;
       if (t >= T) continue;
       float v = epilogue_apply(acc[i][j], ep, b, co, Cout);
@@ -400,26 +413,34 @@ int conv1d_simt_launch(void* dst, int64_t dsb, const void* src, const void* src2
     BVG_CHECK_ARG(T > dil * (K - 1) / 2, "conv1d: reflect padding needs T > pad (T=%lld pad=%d)", (long long)T,
                   dil * (K - 1) / 2);
   if (B == 0 || T == 0) return BVG_OK;
-  // small problems (few output channels, or too few 128 x 128 tiles to fill the GPU) take 64 x 64 tiles
+  // tile choice (fp32 path): channel-exact tiles for the narrow generator stages, 64 x 64 tiles for small problems
+  // (few output channels, or too few 128 x 128 tiles to fill the GPU), 128 x 128 otherwise
+  const bool f32 = in_dtype == BVG_F32 && out_dtype == BVG_F32;
   const int64_t tiles128 = ((T + 127) / 128) * ((Cout + 127) / 128) * B;
-  const bool small = in_dtype == BVG_F32 && out_dtype == BVG_F32 && (Cout <= 64 || tiles128 < 148);
-  const int tile = small ? 64 : 128;
-  BVG_CHECK_ARG(B <= 65535 && (Cout + tile - 1) / tile <= 65535, "conv1d: batch/channel grid too large");
-  dim3 grid((unsigned)((T + tile - 1) / tile), (unsigned)((Cout + tile - 1) / tile), (unsigned)B);
+  int ni = 8, nj = 8;
+  if (f32 && T >= 4096 && (Cout == 96 || Cout == 48 || (Cout > 16 && Cout <= 32))) ni = (int)(Cout + 15) / 16;
+  else if (f32 && (Cout <= 64 || tiles128 < 148)) ni = nj = 4;
+  const int tile_c = 16 * ni, tile_t = 16 * nj;
+  BVG_CHECK_ARG(B <= 65535 && (Cout + tile_c - 1) / tile_c <= 65535, "conv1d: batch/channel grid too large");
+  dim3 grid((unsigned)((T + tile_t - 1) / tile_t), (unsigned)((Cout + tile_c - 1) / tile_c), (unsigned)B);
   EpiDev e = to_dev(ep);
   ProfScope prof(st, (T >= 64 && !ep.prof_other) ? KC_CONV : KC_OTHER);
-  if (small)
-    conv1d_simt_kernel<float, float, 4><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
-                                                              sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);
-  else if (in_dtype == BVG_F32 && out_dtype == BVG_F32)
-    conv1d_simt_kernel<float, float, 8><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src, (const float*)src2,
-                                                              sb, sc, st_, weight_kic, e, Cin, Cout, T, K, dil, pad_mode);
+#define BVG_CONV_F32(NI_, NJ_)                                                                                        \
+  conv1d_simt_kernel<float, float, NI_, NJ_><<<grid, 256, 0, st>>>((float*)dst, dsb, (const float*)src,                \
+                                                                   (const float*)src2, sb, sc, st_, weight_kic, e, Cin, \
+                                                                   Cout, T, K, dil, pad_mode)
+  if (f32 && ni == 6) BVG_CONV_F32(6, 8);
+  else if (f32 && ni == 3) BVG_CONV_F32(3, 8);
+  else if (f32 && ni == 2) BVG_CONV_F32(2, 8);
+  else if (f32 && ni == 4) BVG_CONV_F32(4, 4);
+  else if (f32) BVG_CONV_F32(8, 8);
+#undef BVG_CONV_F32
   else if (in_dtype == BVG_BF16 && out_dtype == BVG_BF16)
-    conv1d_simt_kernel<__nv_bfloat16, __nv_bfloat16, 8><<<grid, 256, 0, st>>>(
+    conv1d_simt_kernel<__nv_bfloat16, __nv_bfloat16, 8, 8><<<grid, 256, 0, st>>>(
         (__nv_bfloat16*)dst, dsb, (const __nv_bfloat16*)src, (const __nv_bfloat16*)src2, sb, sc, st_, weight_kic, e,
         Cin, Cout, T, K, dil, pad_mode);
   else if (in_dtype == BVG_F32 && out_dtype == BVG_BF16)
-    conv1d_simt_kernel<float, __nv_bfloat16, 8><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, dsb, (const float*)src,
+    conv1d_simt_kernel<float, __nv_bfloat16, 8, 8><<<grid, 256, 0, st>>>((__nv_bfloat16*)dst, dsb, (const float*)src,
                                                                    (const float*)src2, sb, sc, st_, weight_kic, e,
                                                                    Cin, Cout, T, K, dil, pad_mode);
   else {
