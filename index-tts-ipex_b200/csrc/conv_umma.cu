@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           for (int tp = 0; tp < ntaps; ++tp) {
             const int slot = resident ? cb * ntaps + tp : ws;
             if (!dry && (!resident || tile == first_tile)) {        // resident weights are waited for once
+              const long long ww0 = P.dbg ? clock64() : 0;
               mbar_wait(&full_w[slot], resident ? 0u : wph);
+              if (P.dbg) dbg_ww += clock64() - ww0;
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
