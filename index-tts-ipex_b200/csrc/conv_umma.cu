@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
   uint64_t* tmem_full = empty_w + kMaxWStages;                    // [2]
   uint64_t* tmem_empty = tmem_full + 2;                           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 2);         // [n_nblk * NB]
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);         // [n_nblk * NB] (+32 pad), 16-byte aligned
 
   const int nacc = P.MT * P.NPH;
   const int acc_cols = nacc * P.NB;
@@ -162,12 +162,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       long long dbg_wx = 0, dbg_ww = 0, dbg_wt = 0, dbg_issue = 0;   // (dbg_issue spans a whole channel block, weight waits included)
       const long long dbg_start = P.dbg ? clock64() : 0;
       for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
-        if (!dry) { DBG_T0(); mbar_wait(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }   // epilogue drained this accumulator stage
+        if (!dry) { DBG_T0(); mbar_wait_backoff(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }   // epilogue drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dbase = tmem_base + (uint32_t)(as * acols);
         for (int cb = 0; cb < n_ci_blk; ++cb) {
           const int nk = min(8, (Cin_p - cb * 64) >> 3) >> 1;       // MMAs along K in this channel block (1..4)
-          if (!dry) { DBG_T0(); mbar_wait(&full_x[xs], xph); DBG_ADD(dbg_wx); }
+          if (!dry) { DBG_T0(); mbar_wait_backoff(&full_x[xs], xph); DBG_ADD(dbg_wx); }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           DBG_T0();
           const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
@@ -248,26 +248,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
       // work items = (accumulator, 32-column group); the two warps of a TMEM lane quarter take alternate items
       const int ngrp = (P.NB + 31) >> 5;
-      for (int item = half; item < nacc * ngrp; item += 2) {
-        const int a = item / ngrp, c0 = (item - a * ngrp) << 5;
+      const bool plain = !cond && !P.relu && !P.post_scale && !P.act;   // generator AMP convs: bias, residuals, scale only
+      const int cs = P.y_tp * 8;                                        // elements between channel chunks
+      for (int a = 0; a < nacc; ++a) {
         const int ms = a / P.NPH, s = a - ms * P.NPH;
         const int64_t q = (int64_t)q0 + ms * 128 + r;
         const int64_t t = q * P.u + s - P.p;
         const bool valid = (t >= 0) && (t < P.Tout);
         const int64_t rowoff = ((int64_t)P.y_row0 + (valid ? t : 0)) * 8;
-        {
+        for (int grp = (half - a * ngrp) & 1; grp < ngrp; grp += 2) {
           // columns [c0, c0+32) of accumulator a (the last group may be 16 wide)
+          const int c0 = grp << 5;
           const int ng = (c0 + 16 < P.NB) ? 4 : 2;                  // 8-channel chunks in this group
           const int cobase = nb * P.NB + c0;
+          const int nok = max(0, min(ng, (P.y_chunks * 8 - cobase + 7) >> 3));   // chunks that exist in the output tensor
+          const int64_t off0 = (int64_t)(cobase >> 3) * cs + rowoff;
           uint4 e1[4], e2[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             e1[g] = make_uint4(0, 0, 0, 0); e2[g] = make_uint4(0, 0, 0, 0);
-            const int co = cobase + 8 * g;
-            if (valid && g < ng && co < P.y_chunks * 8) {
-              const int64_t off = (int64_t)(co >> 3) * P.y_tp * 8 + rowoff;
-              if (r1) e1[g] = *reinterpret_cast<const uint4*>(r1 + off);
-              if (r2) e2[g] = *reinterpret_cast<const uint4*>(r2 + off);
+            if (valid && g < nok) {
+              if (r1) e1[g] = *reinterpret_cast<const uint4*>(r1 + off0 + g * cs);
+              if (r2) e2[g] = *reinterpret_cast<const uint4*>(r2 + off0 + g * cs);
             }
           }
           uint32_t v[32];
@@ -275,10 +277,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           if (ng == 4) tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (!valid) continue;
+          if (plain) {
+            // straight-line code for the four chunks (predicated stores only): the branches of the general path
+            // below cost more than the arithmetic
+            const float scale = P.scale;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + 8 * g), b1 = *reinterpret_cast<const float4*>(bs + c0 + 8 * g + 4);
+              float f[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += __uint_as_float(v[8 * g + j]);
+              float ea[8], eb[8];
+              unpack8(e1[g], ea); unpack8(e2[g], eb);               // zeros when there is no residual
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = ((f[j] + ea[j]) + eb[j]) * scale;
+              uint4 o;
+              o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+              if (g < nok) *reinterpret_cast<uint4*>(yb + off0 + g * cs) = o;
+            }
+            continue;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int co = cobase + 8 * g;
-            if (g >= ng || co >= P.y_chunks * 8) continue;           // padding channels inside the tensor are written as zeros
+            if (g >= nok) continue;                                   // padding channels inside the tensor are written as zeros
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bs[c0 + 8 * g + j];
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             uint4 o;
             o.x = pack2(f[0] * P.scale, f[1] * P.scale); o.y = pack2(f[2] * P.scale, f[3] * P.scale);
             o.z = pack2(f[4] * P.scale, f[5] * P.scale); o.w = pack2(f[6] * P.scale, f[7] * P.scale);
-            *reinterpret_cast<uint4*>(yb + (int64_t)(co >> 3) * P.y_tp * 8 + rowoff) = o;
+            *reinterpret_cast<uint4*>(yb + off0 + g * cs) = o;
           }
         }
       }
@@ -404,7 +426,7 @@ __global__ void from_c8t_kernel(TD* __restrict__ dst, const __nv_bfloat16* __res
 }  // namespace
 
 static size_t umma_fixed_smem(int NB, int n_nblk) {
-  return (size_t)(2 * kMaxXStages + 2 * kMaxWStages + 4) * 8 + 16 + (size_t)NB * n_nblk * 4 + 128;
+  return (size_t)(2 * kMaxXStages + 2 * kMaxWStages + 4) * 8 + 16 + (size_t)NB * n_nblk * 4 + 128 + 128;   // (+32 floats: bias over-read)
 }
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
