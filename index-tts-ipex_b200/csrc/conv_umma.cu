@@ -430,7 +430,12 @@ static size_t umma_fixed_smem(int NB, int n_nblk) {
 }
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
-  const int cap = nph >= 4 ? 128 : 256;                       // NPH * NB (x MT) must fit 512 TMEM columns
+  // NPH * NB (x MT) must fit 512 TMEM columns.  For 256 < Cout <= 512 (stage 1, C = 384) three 128-column blocks beat
+  // two 192-column ones: two accumulator stages fit, so the epilogue of tile i overlaps the MMAs of tile i+1 (measured
+  // 1026-1485 against 963-1396 TFLOP/s); for C = 768 and C = 192 the extra passes over x cancel that gain.
+  // BVG_UMMA_NB_CAP overrides (experiments).
+  static const int cap_env = [] { const char* e = getenv("BVG_UMMA_NB_CAP"); return e ? atoi(e) : 0; }();
+  const int cap = nph >= 4 ? 128 : cap_env > 0 ? cap_env : (Cout > 256 && Cout <= 512) ? 128 : 256;
   const int n = (Cout + cap - 1) / cap;
   int nb = ((Cout + n - 1) / n + 15) / 16 * 16;
   *NB = nb;
