@@ -19,8 +19,9 @@
 // ConvTranspose: one accumulator per output phase).  Epilogue: tcgen05.ld -> +bias +cond
 // +residual(s), *scale -> bf16 -> 16-byte coalesced stores (lane = time row).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (one per TMEM lane quarter).
+// Warp roles (416 threads, persistent CTAs): warp 0 = TMA producer, warps 1..4 = MMA issuers (accumulators dealt
+// out among them, descriptors in uniform registers), warps 5..12 = epilogue (TMEM lane quarter x column half).
+// The narrow stages of the decode do not come here: see conv_umma_fused.cu.
 #include <stdlib.h>
 #include <string.h>
 

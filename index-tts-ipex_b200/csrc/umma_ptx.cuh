@@ -50,34 +50,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;   // descriptor version (Blackwell)
-  return d;          // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE (0)
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -89,39 +61,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// one elected lane of a fully converged warp (CUTLASS elect_one_sync): keeps the surrounding control flow
-// warp-uniform, so descriptors live in uniform registers and tcgen05.mma needs no per-lane serialisation
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-// D[tmem] (+)= A * B with the descriptors given as (lo, shared hi) words; executed by one elected lane of a
-// converged warp, all operands warp-uniform
-__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p, e;\n.reg .b64 da, db;\n"
-      "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-// single-thread form: descriptor hi word (SBO = 128 B, version 1, no swizzle) is an immediate, so only the two
-// lo words and the accumulator address change between MMAs
-__device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
-      "mov.b64 da, {%1, 0x4008};\nmov.b64 db, {%2, 0x4008};\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
-}
-// the same with the election inside: executed by a fully converged warp with warp-uniform operands, so the
-// operands can live in uniform registers and no per-lane broadcast loop is generated around the instruction
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32 accumulate.  The descriptors are given as their low words (start
+// address >> 4 | LBO << 16); the high word (SBO = 128 B, descriptor version 1, no swizzle) is the immediate 0x4008.
+// Executed by a fully converged warp with warp-uniform operands, the election sits inside: the operands can then
+// live in uniform registers and no per-lane broadcast loop is generated around the instruction.
 __device__ __forceinline__ void umma_bf16_imm_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                                     uint32_t accumulate) {
   asm volatile(
@@ -136,17 +79,6 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// NK back-to-back MMAs along K (one per 16 input channels), fully unrolled so that every MMA gets its own
-// uniform registers for the two descriptors and the issue does not serialise on them
-template <int NK>
-__device__ __forceinline__ void issue_k(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum,
-                                        uint32_t astep, uint32_t bstep) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    umma_bf16(d, ad + (uint64_t)(k * astep), bd + (uint64_t)(k * bstep), idesc, k ? 1u : accum);
-  }
 }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
