@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-BVG_F32, BVG_BF16, BVG_F16 = 0, 1, 2
+BVG_F32, BVG_BF16, BVG_F16, BVG_F32X3 = 0, 1, 2, 3
 
 
 class BvgConfig(C.Structure):

@@ -58,7 +58,7 @@ struct ProfScope {
     if (rc__ != BVG_OK) return rc__; \
   } while (0)
 
-static inline size_t dtype_size(int dt) { return dt == BVG_F32 ? 4 : 2; }
+static inline size_t dtype_size(int dt) { return (dt == BVG_F32 || dt == BVG_F32X3) ? 4 : 2; }
 
 // ---- element load/store as float -----------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

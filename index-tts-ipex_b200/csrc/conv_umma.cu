@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const uint32_t astep = 2u * P.XR, bstep = 2u * P.NB;            // 16 input channels further along K
       const int NB = P.NB, MT = P.MT, NPH = P.NPH, dil = P.dil, n_iss = P.n_issuers, ntaps = P.ntaps;
       const int n_ci_blk = P.n_ci_blk, Cin_p = P.Cin_p, resident = P.w_resident, dry = P.dry, transposed = P.transposed;
-      const int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols;
+      const int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols, tap_mod = P.tap_mod;
       const uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
       const uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
       const int first_tile = blockIdx.x;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             const uint32_t accum0 = (cb > 0 || tp >= NPH) ? 1u : 0u;  // taps 0..NPH-1 are the first to touch their accumulator
             if (!transposed) {
               // conv: tap = row shift tp*dil; issuer ii owns time sub-tiles ms = ii, ii + n_issuers, ...
-              const uint32_t a_tp = a_cb + (uint32_t)(tp * dil);
+              const uint32_t a_tp = a_cb + (uint32_t)((tp >= tap_mod ? tp - tap_mod : tp) * dil);
               for (int ms = ii; ms < MT; ms += n_iss) {
                 const uint32_t d = dbase + (uint32_t)(ms * NB);
                 uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
       // work items = (accumulator, 32-column group); the two warps of a TMEM lane quarter take alternate items
       const int ngrp = (P.NB + 31) >> 5;
-      const bool plain = !cond && !P.relu && !P.post_scale && !P.act;   // generator AMP convs: bias, residuals, scale only
+      const bool plain = !cond && !P.relu && !P.post_scale && !P.act && !P.yf;   // generator AMP convs: bias, residuals, scale only
+      float* yfb = P.yf ? P.yf + (int64_t)b * P.Cout * P.Tout : nullptr;           // fp32 plain output (split convs)
+      const float* r1f = P.r1f ? P.r1f + (int64_t)b * P.Cout * P.Tout : nullptr;
+      const float* r2f = P.r2f ? P.r2f + (int64_t)b * P.Cout * P.Tout : nullptr;
       const int cs = P.y_tp * 8;                                        // elements between channel chunks
       for (int a = 0; a < nacc; ++a) {
         const int ms = a / P.NPH, s = a - ms * P.NPH;
@@ -278,6 +281,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           if (ng == 4) tmem_ld16_nowait(tbase + (uint32_t)(a * P.NB + c0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (!valid) continue;
+          if (yfb) {
+            // fp32 [Cout][T] rows: for a fixed channel the 32 lanes write 32 consecutive time steps
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int co = cobase + 8 * g + j;
+                if (g < ng && co < P.Cout) {
+                  float f = __uint_as_float(v[8 * g + j]) + bs[c0 + 8 * g + j];
+                  if (cond) f += cond[co];
+                  const int64_t o = (int64_t)co * P.Tout + t;
+                  if (r1f) f += r1f[o];
+                  if (r2f) f += r2f[o];
+                  yfb[o] = f * P.scale;
+                }
+              }
+            }
+            continue;
+          }
           if (plain) {
             // straight-line code for the four chunks (predicated stores only): the branches of the general path
             // below cost more than the arithmetic
@@ -366,8 +388,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
 
 // torch-layout fp32 weight -> packed bf16 tiles [n_blk][ci_blk][tap][kchunk][NB][8], zero padded.
 // conv: src [Cout][Cin][K]; transposed: src [Cin][Cout][K].
+// split_cp > 0: the 3-term split pack (UmmaLayer::split): Cin / K here are the EFFECTIVE sizes (2*Cp channels, 2*K0 taps),
+// src holds the real [Cout][Cin0][K0] weight.
 __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int Cout, int Cin,
-                                 int K, int transposed, int NB, int n_nblk, int Cin_p) {
+                                 int K, int transposed, int NB, int n_nblk, int Cin_p, int split_cp = 0, int Cin0 = 0,
+                                 int K0 = 0) {
   const int64_t total = (int64_t)n_nblk * Cin_p * NB * K;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // decode i -> (nb, cb, tap, kc, row, e)
@@ -385,8 +410,17 @@ __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* _
     const int row = (int)(rem >> 3), e = (int)(rem & 7);
     const int co = nb * NB + row, ci = cb * 64 + kc * 8 + e;
     float v = 0.f;
-    if (co < Cout && ci < Cin && tap < K)
+    if (split_cp > 0) {
+      const int lo_in = ci >= split_cp, cil = lo_in ? ci - split_cp : ci;   // which half of the input the channel reads
+      const int part = tap / K0, k = tap - part * K0;                        // 0: w_hi taps, 1: w_lo taps
+      if (co < Cout && cil < Cin0 && part < 2) {
+        const float w = src[((int64_t)co * Cin0 + cil) * K0 + k];
+        const float hi = __bfloat162float(__float2bfloat16_rn(w));
+        v = part == 0 ? hi : (lo_in ? 0.f : w - hi);
+      }
+    } else if (co < Cout && ci < Cin && tap < K) {
       v = transposed ? src[((int64_t)ci * Cout + co) * K + tap] : src[((int64_t)co * Cin + ci) * K + tap];
+    }
     dst[i] = __float2bfloat16_rn(v);
   }
 }
@@ -407,6 +441,28 @@ __global__ void to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const TS* __restr
     for (int j = 0; j < 8; ++j) {
       const int c = ch * 8 + j;
       f[j] = (t >= 0 && t < T && c < C) ? to_f<TS>(src[b * sb + c * sc + t * st_]) : 0.f;
+    }
+    uint4 o;
+    o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + ((int64_t)b * chunks * Tp + i) * 8) = o;
+  }
+}
+// fp32 -> [hi | lo] bf16 halves in c8t (UmmaLayer::split): chunks [0, Cp/8) hold bf16(x), chunks [Cp/8, 2Cp/8) hold
+// bf16(x - bf16(x)); halo rows and padding channels are zero
+__global__ void split_to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, int64_t sb, int64_t sc,
+                                    int64_t st_, int C, int Cp8, int chunks, int T, int Tp, int pad) {
+  const int b = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)chunks * Tp; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i / Tp), row = (int)(i % Tp);
+    const int t = row - pad;
+    const bool lo = ch >= Cp8;
+    const int c0 = (lo ? ch - Cp8 : ch) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float x = (t >= 0 && t < T && c < C && ch < 2 * Cp8) ? src[b * sb + c * sc + t * st_] : 0.f;
+      f[j] = lo ? x - __bfloat162float(__float2bfloat16_rn(x)) : x;
     }
     uint4 o;
     o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
@@ -462,10 +518,44 @@ int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout
   return BVG_OK;
 }
 
+int64_t umma_pack_split_elems(int Cout, int Cin, int K) {
+  return umma_pack_elems(Cout, 2 * ((Cin + 7) / 8 * 8), 2 * K, 1);
+}
+
+int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, cudaStream_t st) {
+  int NB, nn;
+  umma_choose_nb(Cout, 1, &NB, &nn);
+  const int Cp = (Cin + 7) / 8 * 8, Ce = 2 * Cp, Ke = 2 * K;
+  const int Cin_p = (Ce + 15) / 16 * 16;
+  const int64_t total = (int64_t)nn * Cin_p * NB * Ke;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  pack_umma_kernel<<<blocks, 256, 0, st>>>(dst, src_torch_layout, Cout, Ce, Ke, 0, NB, nn, Cin_p, Cp, Cin, K);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
+int split_to_c8t_launch(const C8T& dst, const float* src, int64_t sb, int64_t sc, int64_t st_, int C, int64_t B,
+                        cudaStream_t st) {
+  if (B == 0) return BVG_OK;
+  const int Cp = (C + 7) / 8 * 8;
+  BVG_CHECK_ARG(dst.C == 2 * Cp, "split_to_c8t: destination must have 2*roundup8(C) channels");
+  dim3 grid((unsigned)std::min<int64_t>(((int64_t)dst.chunks * dst.Tp + 255) / 256, 4096), (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  split_to_c8t_kernel<<<grid, 256, 0, st>>>(dst.p, src, sb, sc, st_, C, Cp / 8, dst.chunks, dst.T, dst.Tp, dst.pad);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B,
                      cudaStream_t st) {
-  BVG_CHECK_ARG(L.w && x.p && y.p, "conv_umma: null pointer");
-  BVG_CHECK_ARG(x.C == L.Cin && y.C == L.Cout, "conv_umma: channel mismatch (x.C=%d Cin=%d y.C=%d Cout=%d)", x.C, L.Cin, y.C, L.Cout);
+  BVG_CHECK_ARG(L.w && x.p && (y.p || ep.yf32), "conv_umma: null pointer");
+  // split convs (UmmaLayer::split) see 2*roundup8(Cin) input channels and 2*K taps
+  const int Cin_eff = L.split ? 2 * ((L.Cin + 7) / 8 * 8) : L.Cin;
+  const int K_eff = L.split ? 2 * L.K : L.K;
+  BVG_CHECK_ARG(!L.split || (!L.transposed && ep.yf32), "conv_umma: split weights need a Conv1d with fp32 output");
+  BVG_CHECK_ARG(!ep.yf32 || (!ep.res1 && !ep.res2 && !ep.relu && !ep.post_scale && !ep.act && !ep.zero_pads),
+                "conv_umma: the fp32 output epilogue takes bias / cond / fp32 residuals / scale only");
+  BVG_CHECK_ARG(x.C == Cin_eff && y.C == L.Cout, "conv_umma: channel mismatch (x.C=%d Cin=%d y.C=%d Cout=%d)", x.C, Cin_eff, y.C, L.Cout);
   UmmaConvParams P;
   memset(&P, 0, sizeof P);
   const int u = L.transposed ? L.stride : 1;
@@ -473,8 +563,9 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.NPH = L.transposed ? u : 1;
   int n_nblk = 1;
   umma_choose_nb(L.Cout, P.NPH, &P.NB, &n_nblk);
-  P.ntaps = L.K;
-  BVG_CHECK_ARG(L.K <= 16, "conv_umma: at most 16 taps");
+  P.ntaps = K_eff;
+  P.tap_mod = L.split ? L.K : K_eff;
+  BVG_CHECK_ARG(L.K <= 16 && K_eff <= 32, "conv_umma: at most 16 taps (32 with split weights)");
   // time sub-tiles per CTA: every weight tile is shared by MT*128 output rows
   P.MT = L.transposed ? 1 : (P.NB <= 64 ? 4 : 2);
   int halo;
@@ -501,7 +592,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
     BVG_CHECK_ARG(x.pad >= 2, "conv_umma: c8t halo too small");
   }
   P.XR = P.MT * 128 + halo;
-  P.Cin_p = (L.Cin + 15) / 16 * 16;
+  P.Cin_p = (Cin_eff + 15) / 16 * 16;
   BVG_CHECK_ARG(x.chunks * 8 >= P.Cin_p, "conv_umma: input tensor must carry channel padding to a multiple of 16");
   P.n_ci_blk = (P.Cin_p + 63) / 64;
   P.Cout = L.Cout;
@@ -510,6 +601,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.w = L.w;
   P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
+  P.yf = ep.yf32; P.r1f = ep.res1_f32; P.r2f = ep.res2_f32;
   P.dbg = ep.dbg;
   P.dry = ep.dry;
   P.relu = ep.relu; P.post_scale = ep.post_scale; P.post_shift = ep.post_shift; P.act = ep.act;

@@ -58,6 +58,7 @@ struct ConvLayer {
   float* bias = nullptr;  // [Cout] or null
   int Cin = 0, Cout = 0, K = 1;
   __nv_bfloat16* wu = nullptr;   // tcgen05 pack (conv_umma.cu), generator convs only
+  __nv_bfloat16* wx3 = nullptr;  // 3-term split pack for the fp32x3 path (Conv1d layers of the generator)
 };
 struct Tdnn {             // conv -> ReLU -> eval-BN (ECAPA_TDNN.py:126-128)
   ConvLayer conv;
@@ -172,6 +173,12 @@ int make_conv(bvg_plan* P, const std::string& wkey, const std::string& bkey, int
     if (rc == BVG_OK) rc = umma_pack_launch((__nv_bfloat16*)du, raw, Cout, Cin, K, transposed ? 1 : 0, umma_nph, 0);
   }
   L->wu = (__nv_bfloat16*)du;
+  void* dx = nullptr;
+  if (rc == BVG_OK && umma_nph == 1 && !transposed) {
+    rc = dev_alloc(P, &dx, (size_t)umma_pack_split_elems(Cout, Cin, K) * 2);
+    if (rc == BVG_OK) rc = umma_pack_split_launch((__nv_bfloat16*)dx, raw, Cout, Cin, K, 0);
+  }
+  L->wx3 = (__nv_bfloat16*)dx;
   cudaError_t e = cudaStreamSynchronize(0);
   cudaFree(raw);
   if (rc != BVG_OK) return rc;
@@ -361,6 +368,7 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
 
 struct GenWs {
   void *A, *Y, *T1, *T2, *XS;
+  void* X3;                 // [hi | lo] c8t staging of one conv input (fp32x3 path)
   float* cond[9];
   float* spk;
   EcapaWs e;
@@ -380,6 +388,16 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
   }
   const size_t bytes = (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * es;
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
+  g->X3 = nullptr;
+  if (dtype == BVG_F32X3) {
+    size_t x3 = c8t_bytes(B, 2 * ((P->cfg.gpt_dim + 7) / 8 * 8), T0);
+    int64_t Tx = T0;
+    for (int i = 0; i < P->n_stage; ++i) {
+      Tx *= P->cfg.upsample_rates[i];
+      x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i + 1] + 7) / 8 * 8), Tx));
+    }
+    g->X3 = b.take(x3);
+  }
   for (int i = 0; i <= P->n_stage; ++i) g->cond[i] = b.takef(Bm * P->C[i]);
   g->spk = b.takef(Bm * P->cfg.speaker_embedding_dim);
   carve_ecapa(b, Bm, Tm, &g->e);
@@ -395,9 +413,25 @@ int act_launch(void* dst, const void* src, const float* a, const float* b_, int6
   return act1d_launch(dst, src, a, b_, B, Cn, T, dtype, /*precise=*/dtype == BVG_F32 ? 1 : 0, st);
 }
 
+// fp32 conv on the tensor cores: split the fp32 input into [hi | lo] bf16 halves, run the tcgen05 conv on the 3-term
+// split weights, fp32 output with the bias / cond / residual / scale epilogue (UmmaLayer::split)
+int gen_conv_x3(float* dst, const float* src, int64_t sb, int64_t sc, int64_t st_, const ConvLayer& L, const ConvEpilogue& ep,
+                int64_t B, int64_t T, int dil, void* x3buf, cudaStream_t st) {
+  C8T xs = make_c8t(x3buf, 2 * ((L.Cin + 7) / 8 * 8), (int)T);
+  BVG_TRY(split_to_c8t_launch(xs, src, sb, sc, st_, L.Cin, B, st));
+  UmmaLayer u;
+  u.w = L.wx3; u.Cin = L.Cin; u.Cout = L.Cout; u.K = L.K; u.dil = dil; u.split = 1;
+  UmmaEpilogue e;
+  e.bias = L.bias; e.cond = ep.cond; e.cond_B = ep.cond_B; e.scale = ep.scale;
+  e.yf32 = dst; e.res1_f32 = static_cast<const float*>(ep.res1); e.res2_f32 = static_cast<const float*>(ep.res2);
+  return conv_umma_launch(u, xs, make_c8t(nullptr, L.Cout, (int)T), e, B, st);
+}
+
 int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, int64_t B, int64_t T, int dil,
-             int dtype, cudaStream_t st) {
+             int dtype, cudaStream_t st, void* x3buf = nullptr) {
   ep.bias = L.bias;
+  if (x3buf && L.wx3)
+    return gen_conv_x3((float*)dst, (const float*)src, (int64_t)L.Cin * T, T, 1, L, ep, B, T, dil, x3buf, st);
   return conv1d_simt_launch(dst, (int64_t)L.Cout * T, src, nullptr, (int64_t)L.Cin * T, T, 1, L.w, ep, B, L.Cin,
                             L.Cout, T, L.K, dil, 0, dtype, dtype, st);
 }
@@ -820,7 +854,8 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
   BVG_CHECK_ARG(P && latent && workspace, "decode: null argument");
   if (!P->finalized) { set_error("decode: plan not finalised"); return BVG_ERR_STATE; }
   BVG_CHECK_ARG((mel != nullptr) != (spk_in != nullptr), "decode: pass exactly one of mel / spk");
-  BVG_CHECK_ARG(dtype == BVG_F32 || dtype == BVG_BF16, "decode: dtype must be BVG_F32 or BVG_BF16");
+  BVG_CHECK_ARG(dtype == BVG_F32 || dtype == BVG_BF16 || dtype == BVG_F32X3, "decode: dtype must be BVG_F32, BVG_BF16 or BVG_F32X3");
+  BVG_CHECK_ARG(dtype != BVG_F32X3 || P->umma, "decode: BVG_F32X3 needs the plan finalised with tensor-core packs");
   BVG_CHECK_ARG(B >= 1 && T0 >= 1, "decode: empty batch or zero latent frames (B=%lld T0=%lld)", (long long)B, (long long)T0);
   // models.py:205-209: Bm == 2B enters a training-only branch that references an undefined attribute
   BVG_CHECK_ARG(Bm == 1 || Bm == B, "decode: reference mel batch must be 1 or B (got %lld for B=%lld)", (long long)Bm, (long long)B);
@@ -850,12 +885,19 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
   }
   if (dtype == BVG_BF16 && P->umma)
     return decode_bf16_umma(P, latent, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st);
+  // BVG_F32X3: the fp32 path below with the Conv1d layers on the tensor cores (3-term bf16 split); everything else
+  // (Activation1d with libdevice sinf, ConvTranspose1d, speaker encoder, conv_post) is the fp32 CUDA-core code
+  void* x3 = g.X3;
+  if (dtype == BVG_F32X3) dtype = BVG_F32;
   // conv_pre on latent^T (models.py:220-226): read [B,T0,gpt_dim] through strides
   {
     ConvEpilogue ep;
     ep.bias = P->conv_pre.bias; ep.cond = g.cond[0]; ep.cond_B = Bm;
-    BVG_TRY(conv1d_simt_launch(g.XS, (int64_t)P->C[0] * T0, latent, nullptr, T0 * c.gpt_dim, 1, c.gpt_dim,
-                               P->conv_pre.w, ep, B, c.gpt_dim, P->C[0], T0, 7, 1, 0, BVG_F32, dtype, st));
+    if (x3 && P->conv_pre.wx3)
+      BVG_TRY(gen_conv_x3((float*)g.XS, latent, T0 * c.gpt_dim, 1, c.gpt_dim, P->conv_pre, ep, B, T0, 1, x3, st));
+    else
+      BVG_TRY(conv1d_simt_launch(g.XS, (int64_t)P->C[0] * T0, latent, nullptr, T0 * c.gpt_dim, 1, c.gpt_dim,
+                                 P->conv_pre.w, ep, B, c.gpt_dim, P->C[0], T0, 7, 1, 0, BVG_F32, dtype, st));
   }
   int64_t T = T0;
   const float inv_nk = 1.0f / (float)c.num_kernels;
@@ -875,17 +917,17 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
       for (int m = 0; m < 3; ++m) {
         BVG_TRY(act_launch(g.T1, y, R.alpha[2 * m], R.beta[2 * m], B, ch, T, dtype, st));
         ConvEpilogue e1;
-        BVG_TRY(gen_conv(g.T2, g.T1, R.c1[m], e1, B, T, R.dil[m], dtype, st));
+        BVG_TRY(gen_conv(g.T2, g.T1, R.c1[m], e1, B, T, R.dil[m], dtype, st, x3));
         BVG_TRY(act_launch(g.T1, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, ch, T, dtype, st));
         ConvEpilogue e2;
         e2.res1 = y;                              // x = xt + x
         if (m < 2) {
-          BVG_TRY(gen_conv(g.Y, g.T1, R.c2[m], e2, B, T, 1, dtype, st));
+          BVG_TRY(gen_conv(g.Y, g.T1, R.c2[m], e2, B, T, 1, dtype, st, x3));
           y = g.Y;
         } else {                                  // xs += block(x); x = xs / num_kernels (models.py:237-243)
           if (j > 0) e2.res2 = g.XS;
           if (j == c.num_kernels - 1) e2.scale = inv_nk;
-          BVG_TRY(gen_conv(g.XS, g.T1, R.c2[m], e2, B, T, 1, dtype, st));
+          BVG_TRY(gen_conv(g.XS, g.T1, R.c2[m], e2, B, T, 1, dtype, st, x3));
         }
       }
     }

@@ -29,6 +29,11 @@ struct UmmaLayer {
   const float* bias = nullptr;
   int Cin = 0, Cout = 0, K = 1, dil = 1;
   int transposed = 0, stride = 1;
+  // 3-term bf16 split ("fp32x3", the tensor-core form of the fp32 path): x = hi + lo and w = hi + lo in bf16,
+  // y = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi accumulated in fp32 (relative error ~2^-17 per product).  The input
+  // tensor carries the halves as channels [hi (Cp) | lo (Cp)], Cp = Cin rounded up to 8, and the weights are packed
+  // with 2K taps: taps [0,K) = (w_hi | w_hi), taps [K,2K) = (w_lo | 0) at the same shifts.
+  int split = 0;
 };
 
 struct UmmaEpilogue {
@@ -44,6 +49,9 @@ struct UmmaEpilogue {
   int act = 0;                        // 1: tanh after the affine
   int prof_other = 0;                 // account this launch to the "other" profiling class (speaker encoder)
   int zero_pads = 0;                  // also (re)write the output's zero halo rows
+  float* yf32 = nullptr;              // fp32 plain [B,Cout,T] output instead of the c8t tensor (split convs)
+  const float* res1_f32 = nullptr;    // fp32 plain residuals for the fp32 output
+  const float* res2_f32 = nullptr;
   int dry = 0;                        // debug: run only the MMA issue loop (no TMA, waits or epilogue)
   long long* dbg = nullptr;           // optional [grid][8] cycle counters (profiling builds of the tests)
 };
@@ -70,12 +78,19 @@ struct UmmaConvParams {
   int Cin;                            // true input channels (fused activation)
   const float* act_alpha; const float* act_beta;   // fused Activation1d parameters (log scale), or null
   const float* post_scale; const float* post_shift;
+  float* yf; const float* r1f; const float* r2f;    // fp32 plain output / residuals (split convs), else null
+  int tap_mod;                        // tap t reads the input at shift (t % tap_mod) * dil (== ntaps unless split)
 };
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
 int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
                      int nph, cudaStream_t st);
+// split-weight pack (see UmmaLayer::split) of a torch-layout [Cout][Cin][K] fp32 weight
+int64_t umma_pack_split_elems(int Cout, int Cin, int K);
+int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, cudaStream_t st);
+// fp32 [B,C,T] (general strides) -> c8t bf16 with 2*roundup8(C) channels: [hi | lo] halves of every element
+int split_to_c8t_launch(const C8T& dst, const float* src, int64_t sb, int64_t sc, int64_t st_, int C, int64_t B, cudaStream_t st);
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
 // Activation1d -> Conv1d in one kernel for narrow layers; BVG_ERR_STATE (nothing launched) if the layer does not qualify
 int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,

@@ -182,7 +182,9 @@ class BigVGAN(nn.Module):
         self._plan = None
         self._plan_device = None
         self._plan_lock = threading.Lock()
-        self.precision = None          # None: fp32, or bf16 under torch.autocast; "fp32" / "bf16" to force
+        # None: fp32, or bf16 under torch.autocast; "fp32" / "bf16" to force; "fp32x3": fp32 tensors with the Conv1d
+        # layers on the tensor cores (3-term bf16 split, ~2e-6 max-abs against the fp32 path's 5e-7)
+        self.precision = None
 
     # ------------------------------------------------------------------ module plumbing
     def _invalidate(self):
@@ -281,9 +283,9 @@ class BigVGAN(nn.Module):
         p = self.precision
         if p is None:
             p = "bf16" if torch.is_autocast_enabled() else "fp32"
-        if p not in ("fp32", "bf16"):
-            raise RuntimeError(f"precision must be 'fp32' or 'bf16', got {p!r}")
-        return capi.BVG_F32 if p == "fp32" else capi.BVG_BF16
+        if p not in ("fp32", "bf16", "fp32x3"):
+            raise RuntimeError(f"precision must be 'fp32', 'fp32x3' or 'bf16', got {p!r}")
+        return {"fp32": capi.BVG_F32, "bf16": capi.BVG_BF16, "fp32x3": capi.BVG_F32X3}[p]
 
     def workspace_bytes(self, B, T0, Tm, dtype_code=None):
         plan = self._plan

@@ -369,3 +369,37 @@ def test_bf16_path_tiny_lengths_full_config(P, T0):
     assert y.shape == (2, 1, T0 * 1024) and torch.isfinite(y).all()
     snr = O.snr_db(ref.cpu(), y.cpu())
     assert snr >= BF16_SNR_GATE, snr
+
+
+@pytest.mark.parametrize("name", ["full15_tame_T12", "full15_wild_T9", "small_wild_T17_bcast", "small_tame_T1"])
+def test_full_forward_fp32x3_vs_reference_golden(P, golden_dir, name):
+    """fp32 tensors with the Conv1d layers on the tensor cores (x and w split into two bf16 terms, three products
+    accumulated in fp32): must hold the fp32 gate of north_star (max-abs <= 1e-4) against the reference's own
+    forward, like the CUDA-core fp32 path."""
+    g = _load(golden_dir, name)
+    m, sd, h = _model(P, str(g["config"]), int(g["wseed"]), str(g["mode"]))
+    latent, mel = O.synthetic_inputs(h, int(g["B"]), int(g["T0"]), int(g["Tm"]), seed=int(g["iseed"]), Bm=int(g["Bm"]))
+    m.precision = "fp32x3"
+    try:
+        wav = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    finally:
+        m.precision = None
+    assert tuple(wav.shape) == g["wav"].shape and wav.dtype == torch.float32
+    err = float(np.abs(wav.cpu().numpy() - g["wav"]).max())
+    assert err <= FP32_GATE, err
+    assert err <= 2e-5, err          # observed ~2e-6
+
+
+def test_full_size_10s_fp32x3_vs_fp32(P):
+    """BASELINE config 2 shape (B = 1, 10 s): the tensor-core fp32 path against the CUDA-core fp32 path."""
+    m, sd, h = _model(P, "indextts15", 0, "tame")
+    latent, mel = O.synthetic_inputs(h, 1, 235, 281, seed=1)
+    m.precision = "fp32"
+    try:
+        ref = m.decode(latent.cuda(), mel_ref=mel.cuda())
+        m.precision = "fp32x3"
+        y = m.decode(latent.cuda(), mel_ref=mel.cuda())
+    finally:
+        m.precision = None
+    err = float((y - ref).abs().max())
+    assert err <= 2e-5, err

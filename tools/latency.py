@@ -11,7 +11,7 @@ m.load_state_dict(O.make_state_dict(h, 0, "tame"), strict=True)
 m = m.to("cuda").eval(); m.remove_weight_norm()
 lat, mel = O.synthetic_inputs(h, 1, 235, 281, seed=1)
 lat, mel = lat.cuda(), mel.cuda()
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "fp32x3", "bf16"):
     m.precision = prec
     for _ in range(3):
         m.decode(lat, mel_ref=mel)
@@ -25,7 +25,7 @@ for prec in ("fp32", "bf16"):
     P.capi.profile_begin(); m.decode(lat, mel_ref=mel); prof = P.capi.profile_end()
     print(f"{prec}: B=1 x 10.03 s  median {ts[len(ts)//2]:.2f} ms  min {ts[0]:.2f} ms  -> {10.027/ (ts[len(ts)//2]/1e3):.0f} x real time; classes {prof}")
 
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "fp32x3", "bf16"):
     m.precision = prec
     run = m.make_graphed_decode(1, 235, 281)
     for _ in range(3):
