@@ -414,7 +414,7 @@ __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* _
       const int lo_in = ci >= split_cp, cil = lo_in ? ci - split_cp : ci;   // which half of the input the channel reads
       const int part = tap / K0, k = tap - part * K0;                        // 0: w_hi taps, 1: w_lo taps
       if (co < Cout && cil < Cin0 && part < 2) {
-        const float w = src[((int64_t)co * Cin0 + cil) * K0 + k];
+        const float w = transposed ? src[((int64_t)cil * Cout + co) * K0 + k] : src[((int64_t)co * Cin0 + cil) * K0 + k];
         const float hi = __bfloat162float(__float2bfloat16_rn(w));
         v = part == 0 ? hi : (lo_in ? 0.f : w - hi);
       }
@@ -518,18 +518,19 @@ int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout
   return BVG_OK;
 }
 
-int64_t umma_pack_split_elems(int Cout, int Cin, int K) {
-  return umma_pack_elems(Cout, 2 * ((Cin + 7) / 8 * 8), 2 * K, 1);
+int64_t umma_pack_split_elems(int Cout, int Cin, int K, int nph) {
+  return umma_pack_elems(Cout, 2 * ((Cin + 7) / 8 * 8), 2 * K, nph);
 }
 
-int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, cudaStream_t st) {
+int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
+                           int nph, cudaStream_t st) {
   int NB, nn;
-  umma_choose_nb(Cout, 1, &NB, &nn);
+  umma_choose_nb(Cout, nph, &NB, &nn);
   const int Cp = (Cin + 7) / 8 * 8, Ce = 2 * Cp, Ke = 2 * K;
   const int Cin_p = (Ce + 15) / 16 * 16;
   const int64_t total = (int64_t)nn * Cin_p * NB * Ke;
   int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  pack_umma_kernel<<<blocks, 256, 0, st>>>(dst, src_torch_layout, Cout, Ce, Ke, 0, NB, nn, Cin_p, Cp, Cin, K);
+  pack_umma_kernel<<<blocks, 256, 0, st>>>(dst, src_torch_layout, Cout, Ce, Ke, transposed, NB, nn, Cin_p, Cp, Cin, K);
   BVG_LAUNCHED();
   return BVG_OK;
 }
@@ -552,7 +553,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   // split convs (UmmaLayer::split) see 2*roundup8(Cin) input channels and 2*K taps
   const int Cin_eff = L.split ? 2 * ((L.Cin + 7) / 8 * 8) : L.Cin;
   const int K_eff = L.split ? 2 * L.K : L.K;
-  BVG_CHECK_ARG(!L.split || (!L.transposed && ep.yf32), "conv_umma: split weights need a Conv1d with fp32 output");
+  BVG_CHECK_ARG(!L.split || ep.yf32, "conv_umma: split weights need the fp32 output epilogue");
   BVG_CHECK_ARG(!ep.yf32 || (!ep.res1 && !ep.res2 && !ep.relu && !ep.post_scale && !ep.act && !ep.zero_pads),
                 "conv_umma: the fp32 output epilogue takes bias / cond / fp32 residuals / scale only");
   BVG_CHECK_ARG(x.C == Cin_eff && y.C == L.Cout, "conv_umma: channel mismatch (x.C=%d Cin=%d y.C=%d Cout=%d)", x.C, Cin_eff, y.C, L.Cout);
@@ -566,8 +567,16 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.ntaps = K_eff;
   P.tap_mod = L.split ? L.K : K_eff;
   BVG_CHECK_ARG(L.K <= 16 && K_eff <= 32, "conv_umma: at most 16 taps (32 with split weights)");
-  // time sub-tiles per CTA: every weight tile is shared by MT*128 output rows
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    BVG_CUDA(cudaGetDevice(&dev));
+    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // time sub-tiles per CTA: every weight tile is shared by MT*128 output rows; halved while the grid would leave SMs
+  // idle (single-utterance latency: stage 0 of a 10 s utterance has 4 x 3 tiles at MT = 2)
   P.MT = L.transposed ? 1 : (P.NB <= 64 ? 4 : 2);
+  while (P.MT > 1 && (int64_t)((y.T + P.MT * 128 - 1) / (P.MT * 128)) * B * n_nblk < num_sms) P.MT >>= 1;
   int halo;
   if (!L.transposed) {
     BVG_CHECK_ARG(y.T == x.T, "conv_umma: conv keeps the length");
@@ -582,7 +591,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   } else {
     BVG_CHECK_ARG(L.K % u == 0 && (L.K - u) % 2 == 0 && J <= 2, "conv_umma: unsupported ConvTranspose1d K=%d stride=%d", L.K, u);
     BVG_CHECK_ARG(y.T == x.T * u, "conv_umma: ConvTranspose1d output length");
-    for (int k = 0; k < L.K; ++k) { P.tap_shift[k] = (int16_t)((J - 1) - k / u); P.tap_acc[k] = (int16_t)(k % u); }
+    BVG_CHECK_ARG(K_eff <= 16, "conv_umma: ConvTranspose1d tap tables hold 16 entries");
+    for (int t = 0; t < K_eff; ++t) { const int k = t % L.K; P.tap_shift[t] = (int16_t)((J - 1) - k / u); P.tap_acc[t] = (int16_t)(k % u); }
     P.lo = J - 1;
     halo = J - 1;
     P.u = u; P.p = (L.K - u) / 2;
@@ -642,12 +652,6 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   }
   const int64_t ntiles = (int64_t)P.tiles_per_batch * B * n_nblk;
   BVG_CHECK_ARG(ntiles < (1ll << 31), "conv_umma: too many tiles");
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    BVG_CUDA(cudaGetDevice(&dev));
-    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
   ProfScope prof(st, ep.prof_other ? KC_OTHER : (L.transposed ? KC_CONVTR : KC_CONV));
   conv_umma_kernel<<<grid, kThreads, smem, st>>>(P);

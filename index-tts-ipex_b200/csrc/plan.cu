@@ -58,7 +58,7 @@ struct ConvLayer {
   float* bias = nullptr;  // [Cout] or null
   int Cin = 0, Cout = 0, K = 1;
   __nv_bfloat16* wu = nullptr;   // tcgen05 pack (conv_umma.cu), generator convs only
-  __nv_bfloat16* wx3 = nullptr;  // 3-term split pack for the fp32x3 path (Conv1d layers of the generator)
+  __nv_bfloat16* wx3 = nullptr;  // 3-term split pack for the fp32x3 path (generator convs and transposed convs)
 };
 struct Tdnn {             // conv -> ReLU -> eval-BN (ECAPA_TDNN.py:126-128)
   ConvLayer conv;
@@ -174,9 +174,9 @@ int make_conv(bvg_plan* P, const std::string& wkey, const std::string& bkey, int
   }
   L->wu = (__nv_bfloat16*)du;
   void* dx = nullptr;
-  if (rc == BVG_OK && umma_nph == 1 && !transposed) {
-    rc = dev_alloc(P, &dx, (size_t)umma_pack_split_elems(Cout, Cin, K) * 2);
-    if (rc == BVG_OK) rc = umma_pack_split_launch((__nv_bfloat16*)dx, raw, Cout, Cin, K, 0);
+  if (rc == BVG_OK && umma_nph > 0 && 2 * K <= (transposed ? 16 : 32)) {
+    rc = dev_alloc(P, &dx, (size_t)umma_pack_split_elems(Cout, Cin, K, umma_nph) * 2);
+    if (rc == BVG_OK) rc = umma_pack_split_launch((__nv_bfloat16*)dx, raw, Cout, Cin, K, transposed ? 1 : 0, umma_nph, 0);
   }
   L->wx3 = (__nv_bfloat16*)dx;
   cudaError_t e = cudaStreamSynchronize(0);
@@ -394,6 +394,7 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
     int64_t Tx = T0;
     for (int i = 0; i < P->n_stage; ++i) {
       Tx *= P->cfg.upsample_rates[i];
+      x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i] + 7) / 8 * 8), Tx / P->cfg.upsample_rates[i]));   // ups[i] input
       x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i + 1] + 7) / 8 * 8), Tx));
     }
     g->X3 = b.take(x3);
@@ -908,7 +909,19 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
       ConvEpilogue ep;
       ep.bias = P->ups[i].bias;
       if (c.cond_in_each_up_layer) { ep.cond = g.cond[i + 1]; ep.cond_B = Bm; }
-      BVG_TRY(convtr1d_simt_launch(g.A, g.XS, P->ups[i].w, ep, B, P->C[i], ch, T, P->ups[i].K, u, dtype, st));
+      if (x3 && P->ups[i].wx3) {
+        // ConvTranspose1d on the tensor cores as well (phase mode of conv_umma_kernel, split weights)
+        const ConvLayer& L = P->ups[i];
+        C8T xsp = make_c8t(x3, 2 * ((L.Cin + 7) / 8 * 8), (int)T);
+        BVG_TRY(split_to_c8t_launch(xsp, (const float*)g.XS, (int64_t)L.Cin * T, T, 1, L.Cin, B, st));
+        UmmaLayer ul;
+        ul.w = L.wx3; ul.Cin = L.Cin; ul.Cout = L.Cout; ul.K = L.K; ul.dil = 1; ul.transposed = 1; ul.stride = u; ul.split = 1;
+        UmmaEpilogue ue;
+        ue.bias = L.bias; ue.cond = ep.cond; ue.cond_B = ep.cond_B; ue.yf32 = (float*)g.A;
+        BVG_TRY(conv_umma_launch(ul, xsp, make_c8t(nullptr, L.Cout, (int)(T * u)), ue, B, st));
+      } else {
+        BVG_TRY(convtr1d_simt_launch(g.A, g.XS, P->ups[i].w, ep, B, P->C[i], ch, T, P->ups[i].K, u, dtype, st));
+      }
     }
     T *= u;
     for (int j = 0; j < c.num_kernels; ++j) {

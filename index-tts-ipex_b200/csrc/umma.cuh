@@ -87,8 +87,9 @@ int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
                      int nph, cudaStream_t st);
 // split-weight pack (see UmmaLayer::split) of a torch-layout [Cout][Cin][K] fp32 weight
-int64_t umma_pack_split_elems(int Cout, int Cin, int K);
-int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, cudaStream_t st);
+int64_t umma_pack_split_elems(int Cout, int Cin, int K, int nph);
+int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,
+                           int nph, cudaStream_t st);
 // fp32 [B,C,T] (general strides) -> c8t bf16 with 2*roundup8(C) channels: [hi | lo] halves of every element
 int split_to_c8t_launch(const C8T& dst, const float* src, int64_t sb, int64_t sc, int64_t st_, int C, int64_t B, cudaStream_t st);
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
