@@ -283,20 +283,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           if (!valid) continue;
           if (yfb) {
             // fp32 [Cout][T] rows: for a fixed channel the 32 lanes write 32 consecutive time steps
+            const float scale = P.scale;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
+              const int co = cobase + 8 * g;
+              if (g >= ng || co >= P.Cout) continue;
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + c0 + 8 * g), b1 = *reinterpret_cast<const float4*>(bs + c0 + 8 * g + 4);
+              float f[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const int nj = min(8, P.Cout - co);                     // (8 for every layer of the generator)
+              const int64_t o = (int64_t)co * P.Tout + t;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int co = cobase + 8 * g + j;
-                if (g < ng && co < P.Cout) {
-                  float f = __uint_as_float(v[8 * g + j]) + bs[c0 + 8 * g + j];
-                  if (cond) f += cond[co];
-                  const int64_t o = (int64_t)co * P.Tout + t;
-                  if (r1f) f += r1f[o];
-                  if (r2f) f += r2f[o];
-                  yfb[o] = f * P.scale;
-                }
+              for (int j = 0; j < 8; ++j) f[j] += __uint_as_float(v[8 * g + j]);
+              if (cond) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < nj) f[j] += cond[co + j];
               }
+              if (r1f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < nj) f[j] += r1f[o + (int64_t)j * P.Tout];
+              }
+              if (r2f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < nj) f[j] += r2f[o + (int64_t)j * P.Tout];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (j < nj) yfb[o + (int64_t)j * P.Tout] = f[j] * scale;
             }
             continue;
           }

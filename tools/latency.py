@@ -38,3 +38,19 @@ for prec in ("fp32", "fp32x3", "bf16"):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     print(f"{prec} CUDA graph: median {ts[len(ts)//2]:.2f} ms  min {ts[0]:.2f} ms")
+
+# steady-state serving: the speaker embedding of a voice is computed once and reused (decode(..., spk=...))
+m.precision = "fp32"
+spk = m.speaker_embed(mel)
+for prec in ("fp32x3", "bf16"):
+    m.precision = prec
+    for _ in range(3):
+        m.decode(lat, spk=spk)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m.decode(lat, spk=spk); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"{prec} with a cached speaker embedding: median {ts[len(ts)//2]:.2f} ms  min {ts[0]:.2f} ms")
