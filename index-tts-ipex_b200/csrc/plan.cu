@@ -409,9 +409,11 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
   g->pcm_dev = static_cast<int16_t*>(b.take((size_t)B * T0 * P->total_up * 2));
 }
 
+// precise: libdevice sinf (the fp32 parity path); otherwise the packed fast-math stencil (MUFU cosine), which the
+// fp32x3 path can afford inside its 1e-4 budget (BVG_X3_PRECISE_ACT=1 keeps sinf there as well)
 int act_launch(void* dst, const void* src, const float* a, const float* b_, int64_t B, int64_t Cn, int64_t T,
-               int dtype, cudaStream_t st) {
-  return act1d_launch(dst, src, a, b_, B, Cn, T, dtype, /*precise=*/dtype == BVG_F32 ? 1 : 0, st);
+               int dtype, cudaStream_t st, bool fast_f32 = false) {
+  return act1d_launch(dst, src, a, b_, B, Cn, T, dtype, /*precise=*/(dtype == BVG_F32 && !fast_f32) ? 1 : 0, st);
 }
 
 // fp32 conv on the tensor cores: split the fp32 input into [hi | lo] bf16 halves, run the tcgen05 conv on the 3-term
@@ -889,6 +891,8 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
   // BVG_F32X3: the fp32 path below with the Conv1d layers on the tensor cores (3-term bf16 split); everything else
   // (Activation1d with libdevice sinf, ConvTranspose1d, speaker encoder, conv_post) is the fp32 CUDA-core code
   void* x3 = g.X3;
+  static const bool x3_precise = [] { const char* e = getenv("BVG_X3_PRECISE_ACT"); return e && e[0] == '1'; }();
+  const bool fast_act = dtype == BVG_F32X3 && !x3_precise;
   if (dtype == BVG_F32X3) dtype = BVG_F32;
   // conv_pre on latent^T (models.py:220-226): read [B,T0,gpt_dim] through strides
   {
@@ -928,10 +932,10 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
       const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
       const void* y = g.A;                       // AMPBlock1.forward models.py:65-74
       for (int m = 0; m < 3; ++m) {
-        BVG_TRY(act_launch(g.T1, y, R.alpha[2 * m], R.beta[2 * m], B, ch, T, dtype, st));
+        BVG_TRY(act_launch(g.T1, y, R.alpha[2 * m], R.beta[2 * m], B, ch, T, dtype, st, fast_act));
         ConvEpilogue e1;
         BVG_TRY(gen_conv(g.T2, g.T1, R.c1[m], e1, B, T, R.dil[m], dtype, st, x3));
-        BVG_TRY(act_launch(g.T1, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, ch, T, dtype, st));
+        BVG_TRY(act_launch(g.T1, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, ch, T, dtype, st, fast_act));
         ConvEpilogue e2;
         e2.res1 = y;                              // x = xt + x
         if (m < 2) {
@@ -946,7 +950,7 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
     }
   }
   const int chp = P->C[P->n_stage];
-  BVG_TRY(act_launch(g.T1, g.XS, P->post_alpha, P->post_beta, B, chp, T, dtype, st));
+  BVG_TRY(act_launch(g.T1, g.XS, P->post_alpha, P->post_beta, B, chp, T, dtype, st, fast_act));
   BVG_TRY(conv_post_launch(wav, pcm16, g.T1, P->post_w, P->post_bias, B, chp, T, 7, t_lo_pad * P->total_up,
                            t_hi_pad * P->total_up, dtype, st));
   return BVG_OK;
