@@ -168,7 +168,8 @@ BVG_API int bvg_plan_finalize(bvg_plan* plan, int enable_bf16_umma);
 
 /* workspace the decode call needs for (B utterances, T0 latent frames, Tm mel frames) in
  * precision `dtype` (BVG_F32: fp32 storage + fp32 CUDA-core math; BVG_BF16: bf16 storage,
- * tcgen05 bf16 convs with fp32 accumulate) */
+ * tcgen05 bf16 convs with fp32 accumulate; BVG_F32X3: fp32 storage, tcgen05 convs on 3-term
+ * bf16 splits, fast-math Activation1d) */
 BVG_API size_t bvg_workspace_bytes(const bvg_plan* plan, int64_t B, int64_t T0, int64_t Tm, int dtype);
 
 /* speaker encoder only:  mel [Bm, Tm, num_mels] fp32 device -> spk [Bm, emb] fp32 device
