@@ -234,10 +234,37 @@ template <typename T> struct PairSmem {
   static constexpr int kBytes = kPRows * (kInPitch + kOutPitch) + 16;
 };
 
-template <typename T, bool ALIGNED>
+// Split output (fp32x3 path, fp32 input only): instead of fp32 rows the tile leaves as the [hi | lo] bf16 halves of the
+// c8t tensor the split tcgen05 conv reads (UmmaLayer::split), so the activated fp32 tensor never goes through HBM.
+// Staging (in place of the fp32 result rows): [half][8-row group][512 time rows][8 channels] bf16.
+struct SplitOut {
+  __nv_bfloat16* p;     // c8t base, null = plain output
+  int chunks, Tp, pad, Cp8;
+};
+
+template <bool SPLIT, typename T>
+__device__ __forceinline__ void put16(uint8_t* otile_b, int row, int c0, const float (&y)[16]) {
+  if (!SPLIT) {
+    T* o = reinterpret_cast<T*>(otile_b + row * PairSmem<T>::kOutPitch) + c0;
+    store8_vec<T>(o, *reinterpret_cast<const float(*)[8]>(&y[0]));
+    store8_vec<T>(o + 8, *reinterpret_cast<const float(*)[8]>(&y[8]));
+  } else {
+    __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(otile_b);
+    const int grp = row >> 3, pch = row & 7;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(y[q]);
+      st[((size_t)(0 * 2 + grp) * kPW + c0 + q) * 8 + pch] = hi;
+      st[((size_t)(1 * 2 + grp) * kPW + c0 + q) * 8 + pch] = __float2bfloat16_rn(y[q] - __bfloat162float(hi));
+    }
+  }
+}
+
+template <typename T, bool ALIGNED, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 3)
 act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* __restrict__ alpha_log,
-                  const float* __restrict__ beta_log, int64_t rows, int C, int64_t Tlen, int col_tiles) {
+                  const float* __restrict__ beta_log, int64_t rows, int C, int64_t Tlen, int col_tiles,
+                  SplitOut sp = SplitOut{nullptr, 0, 0, 0, 0}) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int IP = PairSmem<T>::kInPitch, OP = PairSmem<T>::kOutPitch;
   uint8_t* tile_b = smem_raw;                                     // [kPRows] rows of IP bytes
@@ -320,10 +347,8 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
         },
         [&](int q, float va_, float vb_) { ya[q] = va_; yb[q] = vb_; },
         pk2(a0, a1), pk2(b0, b1));
-    store8_vec<T>(otile(r) + c0, *reinterpret_cast<float(*)[8]>(&ya[0]));
-    store8_vec<T>(otile(r) + c0 + 8, *reinterpret_cast<float(*)[8]>(&ya[8]));
-    store8_vec<T>(otile(r2) + c0, *reinterpret_cast<float(*)[8]>(&yb[0]));
-    store8_vec<T>(otile(r2) + c0 + 8, *reinterpret_cast<float(*)[8]>(&yb[8]));
+    put16<SPLIT, T>(otile_b, r, c0, ya);
+    put16<SPLIT, T>(otile_b, r2, c0, yb);
   } else {
     for (int h = 0; h < nr; ++h) {          // sequence edges / odd last row: scalar stencil with replicate padding
       const int rr = h ? r2 : r;
@@ -331,13 +356,43 @@ act1d_pair_kernel(T* __restrict__ dst, const T* __restrict__ src, const float* _
 #pragma unroll
       for (int j = 0; j < V + 16; ++j) xw[j] = to_f<T>(tile(rr)[c0 + j]);
       act1d_window<V, false>(xw, y, h ? a1 : a0, h ? b1 : b0, tg, Tlen);
+      if (SPLIT) {
+        put16<SPLIT, T>(otile_b, rr, c0, y);
+      } else {
 #pragma unroll
-      for (int q = 0; q < V; ++q) otile(rr)[c0 + q] = from_f<T>(y[q]);
+        for (int q = 0; q < V; ++q) otile(rr)[c0 + q] = from_f<T>(y[q]);
+      }
     }
   }
   }
   // results leave row by row: TMA bulk stores when rows are 16-byte aligned, coalesced stores otherwise
   const int ncols = (int)min((int64_t)kPW, Tlen - t0);
+  if (SPLIT) {
+    // four chunk tiles (half x 8-row group), each a contiguous run of ncols 16-byte rows in the c8t tensor
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    auto chunk_base = [&](int ct) -> __nv_bfloat16* {               // ct = half * 2 + group; row t = 0 of that chunk
+      const int64_t R = row0 + (ct & 1) * 8;
+      const int64_t b = R / C, ch = (R % C) >> 3;
+      return sp.p + (((int64_t)b * sp.chunks + (ct >> 1) * sp.Cp8 + ch) * sp.Tp + sp.pad) * 8;
+    };
+    if (tid < 4 && (tid & 1) * 8 < nrows) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(chunk_base(tid) + t0 * 8),
+                   "r"(smem_u32(otile_b + (size_t)tid * kPW * 16)), "r"((uint32_t)(ncols * 16)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // the c8t zero halo rows in front of t = 0 and behind t = T-1 (the conv's zero padding) come from the edge tiles
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (tid >= 128 && tid < 128 + 4 * 32) {
+      const int ct = (tid - 128) >> 5, rowi = (tid - 128) & 31;
+      if ((ct & 1) * 8 < nrows && rowi < sp.pad) {
+        if (t0 == 0) *reinterpret_cast<uint4*>(chunk_base(ct) + ((int64_t)rowi - sp.pad) * 8) = z;
+        if (t0 + kPW >= Tlen) *reinterpret_cast<uint4*>(chunk_base(ct) + (Tlen + rowi) * 8) = z;
+      }
+    }
+    if (tid < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    return;
+  }
   if (ALIGNED) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -382,6 +437,32 @@ int launch_pair(void* dst, const void* src, const float* a, const float* b, int6
 }
 
 }  // namespace
+
+// Activation1d on fp32 [B,C,T] with the result written as the [hi | lo] bf16 c8t tensor of the split convs.
+// BVG_ERR_STATE (nothing launched) when the shape does not qualify (C % 8, T % 16, 16-byte alignment).
+int act1d_split_launch(__nv_bfloat16* dst_c8t, int dst_chunks, int dst_Tp, int dst_pad, const float* src,
+                       const float* alpha_log, const float* beta_log, int64_t B, int64_t C, int64_t T, cudaStream_t st) {
+  if (B == 0 || T == 0) return BVG_OK;
+  if (C % 8 != 0 || T % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_c8t) & 15))
+    return BVG_ERR_STATE;
+  BVG_CHECK_ARG(dst_chunks == 2 * (int)(C / 8) && dst_Tp == T + 2 * dst_pad, "act1d_split: destination geometry");
+  const int64_t rows = B * C;
+  const int64_t col_tiles = (T + kPW - 1) / kPW, row_groups = (rows + kPRows - 1) / kPRows;
+  const int64_t nblk = col_tiles * row_groups;
+  BVG_CHECK_ARG(nblk < (1ll << 31), "act1d_split: problem too large");
+  const size_t smem = PairSmem<float>::kBytes;
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  SplitOut sp{dst_c8t, dst_chunks, dst_Tp, dst_pad, (int)(C / 8)};
+  ProfScope prof(st, KC_ACT1D);
+  act1d_pair_kernel<float, true, true><<<(unsigned)nblk, 256, smem, st>>>(nullptr, src, alpha_log, beta_log, rows, (int)C, T,
+                                                                         (int)col_tiles, sp);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
 
 int act1d_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                  int64_t B, int64_t C, int64_t T, int dtype, int precise, cudaStream_t st) {

@@ -81,6 +81,9 @@ template <> __device__ __forceinline__ __half from_f<__half>(float v) { return _
 #define BVG_F5 0x1.c5d8cap-2f
 
 // internal launchers (defined in the .cu files), all enqueue on `st`
+// Activation1d (fast-math) on fp32 [B,C,T], written as the [hi | lo] bf16 c8t tensor the split convs read (fp32x3 path)
+int act1d_split_launch(__nv_bfloat16* dst_c8t, int dst_chunks, int dst_Tp, int dst_pad, const float* src,
+                       const float* alpha_log, const float* beta_log, int64_t B, int64_t C, int64_t T, cudaStream_t st);
 int act1d_launch(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                  int64_t B, int64_t C, int64_t T, int dtype, int precise, cudaStream_t st);
 

@@ -421,13 +421,23 @@ int act_launch(void* dst, const void* src, const float* a, const float* b_, int6
 int gen_conv_x3(float* dst, const float* src, int64_t sb, int64_t sc, int64_t st_, const ConvLayer& L, const ConvEpilogue& ep,
                 int64_t B, int64_t T, int dil, void* x3buf, cudaStream_t st) {
   C8T xs = make_c8t(x3buf, 2 * ((L.Cin + 7) / 8 * 8), (int)T);
-  BVG_TRY(split_to_c8t_launch(xs, src, sb, sc, st_, L.Cin, B, st));
+  if (src) BVG_TRY(split_to_c8t_launch(xs, src, sb, sc, st_, L.Cin, B, st));   // (null: x3buf already holds the split input)
   UmmaLayer u;
   u.w = L.wx3; u.Cin = L.Cin; u.Cout = L.Cout; u.K = L.K; u.dil = dil; u.split = 1;
   UmmaEpilogue e;
   e.bias = L.bias; e.cond = ep.cond; e.cond_B = ep.cond_B; e.scale = ep.scale;
   e.yf32 = dst; e.res1_f32 = static_cast<const float*>(ep.res1); e.res2_f32 = static_cast<const float*>(ep.res2);
   return conv_umma_launch(u, xs, make_c8t(nullptr, L.Cout, (int)T), e, B, st);
+}
+
+// fp32x3: Activation1d written straight into the split c8t tensor, then the split conv (no fp32 round trip through HBM)
+int act_conv_x3(float* dst, const float* src, const float* alpha, const float* beta, const ConvLayer& L, ConvEpilogue ep,
+                int64_t B, int64_t T, int dil, void* x3buf, cudaStream_t st) {
+  C8T xs = make_c8t(x3buf, 2 * ((L.Cin + 7) / 8 * 8), (int)T);
+  const int rc = act1d_split_launch(xs.p, xs.chunks, xs.Tp, xs.pad, src, alpha, beta, B, L.Cin, T, st);
+  if (rc != BVG_OK) return rc;                      // BVG_ERR_STATE: shape does not qualify, the caller takes the 2-step route
+  ep.bias = L.bias;
+  return gen_conv_x3(dst, nullptr, 0, 0, 0, L, ep, B, T, dil, x3buf, st);
 }
 
 int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, int64_t B, int64_t T, int dil,
@@ -932,19 +942,27 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
       const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
       const void* y = g.A;                       // AMPBlock1.forward models.py:65-74
       for (int m = 0; m < 3; ++m) {
-        BVG_TRY(act_launch(g.T1, y, R.alpha[2 * m], R.beta[2 * m], B, ch, T, dtype, st, fast_act));
+        // act -> conv: one pass through the split tensor on the fp32x3 path when the shape qualifies
+        auto act_conv = [&](void* dst, const void* src, const float* al, const float* be, const ConvLayer& L, const ConvEpilogue& e,
+                            int dil) -> int {
+          if (x3 && fast_act && L.wx3) {
+            const int rc = act_conv_x3((float*)dst, (const float*)src, al, be, L, e, B, T, dil, x3, st);
+            if (rc != BVG_ERR_STATE) return rc;
+          }
+          BVG_TRY(act_launch(g.T1, src, al, be, B, ch, T, dtype, st, fast_act));
+          return gen_conv(dst, g.T1, L, e, B, T, dil, dtype, st, x3);
+        };
         ConvEpilogue e1;
-        BVG_TRY(gen_conv(g.T2, g.T1, R.c1[m], e1, B, T, R.dil[m], dtype, st, x3));
-        BVG_TRY(act_launch(g.T1, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, ch, T, dtype, st, fast_act));
+        BVG_TRY(act_conv(g.T2, y, R.alpha[2 * m], R.beta[2 * m], R.c1[m], e1, R.dil[m]));
         ConvEpilogue e2;
         e2.res1 = y;                              // x = xt + x
         if (m < 2) {
-          BVG_TRY(gen_conv(g.Y, g.T1, R.c2[m], e2, B, T, 1, dtype, st, x3));
+          BVG_TRY(act_conv(g.Y, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
           y = g.Y;
         } else {                                  // xs += block(x); x = xs / num_kernels (models.py:237-243)
           if (j > 0) e2.res2 = g.XS;
           if (j == c.num_kernels - 1) e2.scale = inv_nk;
-          BVG_TRY(gen_conv(g.XS, g.T1, R.c2[m], e2, B, T, 1, dtype, st, x3));
+          BVG_TRY(act_conv(g.XS, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
         }
       }
     }
