@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const int NB = P.NB, MT = P.MT, NPH = P.NPH, dil = P.dil, n_iss = P.n_issuers, ntaps = P.ntaps;
       const int n_ci_blk = P.n_ci_blk, Cin_p = P.Cin_p, resident = P.w_resident, dry = P.dry, transposed = P.transposed;
       const int n_xst = kXStages, n_wst = kWStages, n_ast = P.acc_stages, acols = acc_cols, tap_mod = P.tap_mod;
+      const int hi_chunks = P.split_hi_chunks;
       const uint32_t xsb16 = x_stage_bytes >> 4, wslot16 = w_stage_bytes >> 4;
       const uint32_t x_base = (smem_u32(xsm) >> 4) | a_lbo, w_base = (smem_u32(wsm) >> 4) | b_lbo;
       const int first_tile = blockIdx.x;
@@ -182,14 +183,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             }
             const uint32_t b_lo = w_base + (uint32_t)slot * wslot16;
             const uint32_t accum0 = (cb > 0 || tp >= NPH) ? 1u : 0u;  // taps 0..NPH-1 are the first to touch their accumulator
+            // split convs: the w_lo taps (tp >= tap_mod) multiply the lo half of the input by zero weights -- skip those MMAs
+            const int nk_t = (hi_chunks > 0 && tp >= tap_mod) ? max(0, min(nk, (hi_chunks - cb * 8 + 1) >> 1)) : nk;
             if (!transposed) {
               // conv: tap = row shift tp*dil; issuer ii owns time sub-tiles ms = ii, ii + n_issuers, ...
               const uint32_t a_tp = a_cb + (uint32_t)((tp >= tap_mod ? tp - tap_mod : tp) * dil);
               for (int ms = ii; ms < MT; ms += n_iss) {
                 const uint32_t d = dbase + (uint32_t)(ms * NB);
                 uint32_t am = a_tp + (uint32_t)(ms * 128), bm = b_lo;
-                umma_bf16_imm_elect(d, am, bm, idesc, accum0);
-                for (int k = 1; k < nk; ++k) {
+                if (nk_t > 0) umma_bf16_imm_elect(d, am, bm, idesc, accum0);
+                for (int k = 1; k < nk_t; ++k) {
                   am += astep; bm += bstep;
                   umma_bf16_imm_elect(d, am, bm, idesc, 1u);
                 }
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
               // ConvTranspose: one accumulator per output phase, issuer ii owns phases == ii (mod n_issuers)
               const uint32_t d = dbase + (uint32_t)(P.tap_acc[tp] * NB);
               uint32_t am = a_cb + (uint32_t)P.tap_shift[tp], bm = b_lo;
-              umma_bf16_imm_elect(d, am, bm, idesc, accum0);
-              for (int k = 1; k < nk; ++k) {
+              if (nk_t > 0) umma_bf16_imm_elect(d, am, bm, idesc, accum0);
+              for (int k = 1; k < nk_t; ++k) {
                 am += astep; bm += bstep;
                 umma_bf16_imm_elect(d, am, bm, idesc, 1u);
               }
@@ -577,6 +580,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   umma_choose_nb(L.Cout, P.NPH, &P.NB, &n_nblk);
   P.ntaps = K_eff;
   P.tap_mod = L.split ? L.K : K_eff;
+  P.split_hi_chunks = L.split ? (L.Cin + 7) / 8 : 0;
   BVG_CHECK_ARG(L.K <= 16 && K_eff <= 32, "conv_umma: at most 16 taps (32 with split weights)");
   static int num_sms = 0;
   if (!num_sms) {

@@ -80,6 +80,7 @@ struct UmmaConvParams {
   const float* post_scale; const float* post_shift;
   float* yf; const float* r1f; const float* r2f;    // fp32 plain output / residuals (split convs), else null
   int tap_mod;                        // tap t reads the input at shift (t % tap_mod) * dil (== ntaps unless split)
+  int split_hi_chunks;                // split convs: 8-channel chunks of the hi half (taps >= tap_mod have zero weights beyond), else 0
 };
 
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
