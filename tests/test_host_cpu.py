@@ -99,3 +99,52 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_dtype_codes_match_header(P):
+    hdr = open(os.path.join(ROOT, "include", "bigvgan_b200.h")).read()
+    m = re.search(r"enum \{ BVG_F32 = (\d+), BVG_BF16 = (\d+), BVG_F16 = (\d+), BVG_F32X3 = (\d+) \};", hdr)
+    assert m, "dtype enum not found in the header"
+    assert tuple(int(v) for v in m.groups()) == (P.capi.BVG_F32, P.capi.BVG_BF16, P.capi.BVG_F16, P.capi.BVG_F32X3)
+    h = O.small_config()
+    m_ = P.BigVGAN(h, use_cuda_kernel=True)
+    for prec, code in (("fp32", P.capi.BVG_F32), ("bf16", P.capi.BVG_BF16), ("fp32x3", P.capi.BVG_F32X3)):
+        m_.precision = prec
+        assert m_._dtype_code() == code
+    m_.precision = "fp16"
+    with pytest.raises(RuntimeError):
+        m_._dtype_code()
+
+
+def test_decode_ragged_grouping_logic(P):
+    """Host logic of decode_ragged without a GPU: equal lengths are batched together, one speaker-encoder pass per
+    distinct reference, outputs come back in input order."""
+    h = O.small_config()
+    m = P.BigVGAN(h, use_cuda_kernel=True)
+    calls = {"spk": 0, "decode": []}
+
+    def fake_spk(mel):
+        calls["spk"] += 1
+        return mel.mean(dim=(1, 2), keepdim=True).expand(-1, 1, int(h.speaker_embedding_dim)).clone()
+
+    def fake_decode(x, mel_ref=None, spk=None, pcm16=False, halo=(0, 0), workspace=None):
+        calls["decode"].append(tuple(x.shape))
+        # "waveform" = per-utterance latent mean + speaker mean, repeated over T0 * upsample samples
+        v = x.mean(dim=(1, 2)) + spk.reshape(x.shape[0], -1).mean(dim=1)
+        return v.view(-1, 1, 1).expand(-1, 1, x.shape[1] * m.total_upsample).clone()
+
+    m.speaker_embed, m.decode = fake_spk, fake_decode
+    gen = torch.Generator().manual_seed(0)
+    lens = [4, 7, 4, 2, 7]
+    lats = [torch.randn(t, int(h.gpt_dim), generator=gen) for t in lens]
+    mel_a, mel_b = torch.randn(9, int(h.num_mels), generator=gen), torch.randn(11, int(h.num_mels), generator=gen)
+    mels = [mel_a, mel_b, mel_a, mel_b, mel_a]
+    outs = m.decode_ragged(lats, mels)
+    assert calls["spk"] == 2
+    assert sorted(calls["decode"]) == sorted([(2, 4, int(h.gpt_dim)), (2, 7, int(h.gpt_dim)), (1, 2, int(h.gpt_dim))])
+    for x, mel, y in zip(lats, mels, outs):
+        assert y.shape == (1, x.shape[0] * m.total_upsample)
+        assert torch.allclose(y[0, 0], x.mean() + mel.mean())
+    assert m.decode_ragged([], mels) == []
+    with pytest.raises(RuntimeError):
+        m.decode_ragged(lats, mels[:2])
