@@ -113,6 +113,11 @@ BVG_API int bvg_convtr1d_fwd(void* dst, const void* src, const float* weight, co
  * converts internally; test entry point). */
 BVG_API int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                       int64_t B, int64_t C, int64_t T, void* stream);
+/* Same, choosing the implementation: 0 = what the decode path takes (tensor-core FIRs, csrc/act1d_tc.cu, for T >= 256;
+ * the CUDA-core stencil otherwise), 1 = CUDA-core stencil (csrc/act1d_c8t.cu), 2 = tensor-core FIRs (BVG_ERR_INVALID if
+ * the shape does not qualify).  Both follow alias_free_torch/act.py:24-29 of the reference, edges included. */
+BVG_API int bvg_act1d_c8t_impl_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                           int64_t B, int64_t C, int64_t T, int impl, void* stream);
 /* Profiling aid: when non-NULL, the next bvg_conv*_umma_fwd launches write 8 int64 cycle counters per CTA
  * (148 CTAs max) into this device buffer: producer wait, MMA waits on input / weights / TMEM, MMA issue,
  * MMA-thread total, epilogue wait, epilogue busy. */

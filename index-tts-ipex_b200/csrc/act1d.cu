@@ -20,6 +20,7 @@
 // registers, one 128-bit coalesced store.  HBM sees each element once in, once out.
 #include "bvg_common.cuh"
 #include "act1d_core.cuh"
+#include "umma_ptx.cuh"
 
 namespace bvg {
 
@@ -30,40 +31,6 @@ constexpr int kW = 256;       // outputs per row per CTA
 constexpr int kHalo = 8;      // staged halo per side (5 needed; 8 keeps 16B alignment)
 constexpr int kPitch = kW + 2 * kHalo;   // 272 elements
 constexpr int kThreads = 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// TMA bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 
 template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
 
@@ -421,12 +388,9 @@ int launch_pair(void* dst, const void* src, const float* a, const float* b, int6
   const bool aligned = (Tlen % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   const size_t smem = PairSmem<T>::kBytes;
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static std::atomic<uint64_t> opted_a{0}, opted_u{0};
+  BVG_TRY(smem_opt_in(act1d_pair_kernel<T, true>, opted_a, (int)smem));
+  BVG_TRY(smem_opt_in(act1d_pair_kernel<T, false>, opted_u, (int)smem));
   ProfScope prof(st, KC_ACT1D);
   T* d = static_cast<T*>(dst);
   const T* s = static_cast<const T*>(src);
@@ -451,11 +415,8 @@ int act1d_split_launch(__nv_bfloat16* dst_c8t, int dst_chunks, int dst_Tp, int d
   const int64_t nblk = col_tiles * row_groups;
   BVG_CHECK_ARG(nblk < (1ll << 31), "act1d_split: problem too large");
   const size_t smem = PairSmem<float>::kBytes;
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(act1d_pair_kernel<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  BVG_TRY(smem_opt_in(act1d_pair_kernel<float, true, true>, opted, (int)smem));
   SplitOut sp{dst_c8t, dst_chunks, dst_Tp, dst_pad, (int)(C / 8)};
   ProfScope prof(st, KC_ACT1D);
   act1d_pair_kernel<float, true, true><<<(unsigned)nblk, 256, smem, st>>>(nullptr, src, alpha_log, beta_log, rows, (int)C, T,

@@ -14,36 +14,10 @@
 #include "act1d_core.cuh"
 #include "bvg_common.cuh"
 #include "umma.cuh"
+#include "umma_ptx.cuh"
 
 namespace bvg {
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // Thread = one 32-bit word (2 channels) x 16 consecutive rows; warp = 4 words x NCH chunks x (8/NCH) row groups.
 template <int NCH>
@@ -193,11 +167,8 @@ template <int NCH>
 int launch_act(const C8T& y, const C8T& x, const float* a, const float* b_, int64_t B, cudaStream_t st) {
   constexpr int TR = 1024 / NCH;
   const size_t smem = (size_t)NCH * (TR + 17) * 16 + (size_t)NCH * (TR + 1) * 16 + 16;
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(act1d_c8t_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  BVG_TRY(smem_opt_in(act1d_c8t_kernel<NCH>, opted, (int)smem));
   dim3 grid((unsigned)((x.Tp + TR - 1) / TR), (unsigned)((x.chunks + NCH - 1) / NCH), (unsigned)B);
   ProfScope prof(st, KC_ACT1D);
   act1d_c8t_kernel<NCH><<<grid, 256, smem, st>>>(y.p, x.p, a, b_, x.C, x.chunks, x.T, x.Tp, x.pad);
@@ -208,10 +179,16 @@ int launch_act(const C8T& y, const C8T& x, const float* a, const float* b_, int6
 }  // namespace
 
 int act1d_c8t_launch(const C8T& y, const C8T& x, const float* alpha_log, const float* beta_log, int64_t B,
-                     cudaStream_t st) {
+                     cudaStream_t st, int impl) {
   BVG_CHECK_ARG(y.p && x.p && y.p != x.p, "act1d_c8t: bad buffers");
   BVG_CHECK_ARG(y.C == x.C && y.T == x.T && y.chunks == x.chunks && y.pad == x.pad, "act1d_c8t: geometry mismatch");
   BVG_CHECK_ARG(B >= 1 && B <= 65535, "act1d_c8t: bad batch");
+  // tensor-core FIRs (act1d_tc.cu) for everything but short tensors; BVG_ACT_TC=0 keeps the CUDA-core stencil (A/B runs)
+  if (impl == 2 || (impl == 0 && BVG_ENV_ONCE("BVG_ACT_TC", 1))) {
+    const int rc = act1d_tc_launch(y, x, alpha_log, beta_log, B, st);
+    if (rc != BVG_ERR_STATE) return rc;
+    BVG_CHECK_ARG(impl != 2, "act1d_c8t: this tensor does not qualify for the tensor-core kernel (T >= 256 required)");
+  }
   if (x.chunks % 8 == 0 || x.chunks > 16) return launch_act<8>(y, x, alpha_log, beta_log, B, st);
   if (x.chunks % 4 == 0) return launch_act<4>(y, x, alpha_log, beta_log, B, st);
   return launch_act<2>(y, x, alpha_log, beta_log, B, st);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <atomic>
 
 #include "../../include/bigvgan_b200.h"
 
@@ -57,6 +58,26 @@ struct ProfScope {
     int rc__ = (call);           \
     if (rc__ != BVG_OK) return rc__; \
   } while (0)
+
+// ---- per-device caches ----------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only and one process may hold plans
+// on several devices (the reference web UI is one process): remember the opt-in per device, not per process.
+template <class Kern>
+inline int smem_opt_in(Kern kern, std::atomic<uint64_t>& done_mask, int bytes) {
+  int dev = 0;
+  BVG_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(done_mask.load(std::memory_order_acquire) & bit)) {
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done_mask.fetch_or(bit, std::memory_order_release);
+  }
+  return BVG_OK;
+}
+// SM count of the current device (cached per device; plan.cu)
+int current_device_sms(int* sms);
+// integer environment switch, read ONCE per process per call site (tuning knobs only)
+int env_int_once(const char* name, int dflt);
+#define BVG_ENV_ONCE(name, dflt) ([]() -> int { static const int v__ = bvg::env_int_once(name, dflt); return v__; }())
 
 static inline size_t dtype_size(int dt) { return (dt == BVG_F32 || dt == BVG_F32X3) ? 4 : 2; }
 

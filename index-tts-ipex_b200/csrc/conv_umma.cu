@@ -505,7 +505,7 @@ void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk) {
   // two 192-column ones: two accumulator stages fit, so the epilogue of tile i overlaps the MMAs of tile i+1 (measured
   // 1026-1485 against 963-1396 TFLOP/s); for C = 768 and C = 192 the extra passes over x cancel that gain.
   // BVG_UMMA_NB_CAP overrides (experiments).
-  static const int cap_env = [] { const char* e = getenv("BVG_UMMA_NB_CAP"); return e ? atoi(e) : 0; }();
+  const int cap_env = BVG_ENV_ONCE("BVG_UMMA_NB_CAP", 0);
   const int cap = nph >= 4 ? 128 : cap_env > 0 ? cap_env : (Cout > 256 && Cout <= 512) ? 128 : 256;
   const int n = (Cout + cap - 1) / cap;
   int nb = ((Cout + n - 1) / n + 15) / 16 * 16;
@@ -582,12 +582,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.tap_mod = L.split ? L.K : K_eff;
   P.split_hi_chunks = L.split ? (L.Cin + 7) / 8 : 0;
   BVG_CHECK_ARG(L.K <= 16 && K_eff <= 32, "conv_umma: at most 16 taps (32 with split weights)");
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    BVG_CUDA(cudaGetDevice(&dev));
-    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  BVG_TRY(current_device_sms(&num_sms));
   // time sub-tiles per CTA: every weight tile is shared by MT*128 output rows; halved while the grid would leave SMs
   // idle (single-utterance latency: stage 0 of a 10 s utterance has 4 x 3 tiles at MT = 2)
   P.MT = L.transposed ? 1 : (P.NB <= 64 ? 4 : 2);
@@ -642,7 +638,7 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.B = (int)B;
   P.n_issuers = 1;
   while (P.n_issuers * 2 <= std::min(kMaxIssuers, P.MT * P.NPH)) P.n_issuers *= 2;   // power of two
-  if (const char* e = getenv("BVG_UMMA_ISSUERS")) P.n_issuers = std::max(1, std::min(P.n_issuers, atoi(e)));
+  if (const int e = BVG_ENV_ONCE("BVG_UMMA_ISSUERS", 0)) P.n_issuers = std::max(1, std::min(P.n_issuers, e));
   // shared-memory plan: keep the whole layer's weights resident when they fit next to >= 2 input stages,
   // otherwise stream them through as deep a ring as fits
   P.kc_max = std::min(8, P.Cin_p / 8);
@@ -660,11 +656,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
     P.w_stages = (int)std::min<size_t>(kMaxWStages, (budget - 2 * xsb) / wsb);
   }
   const size_t smem = (size_t)P.x_stages * xsb + (size_t)P.w_stages * wsb + umma_fixed_smem(P.NB, n_nblk);
-  static bool attr_set = false;
-  if (!attr_set) {
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  BVG_TRY(smem_opt_in(conv_umma_kernel, opted, 227 * 1024));
   const int64_t ntiles = (int64_t)P.tiles_per_batch * B * n_nblk;
   BVG_CHECK_ARG(ntiles < (1ll << 31), "conv_umma: too many tiles");
   dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));

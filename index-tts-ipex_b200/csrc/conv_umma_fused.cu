@@ -470,11 +470,6 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
   }
 }
 
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
-
 }  // namespace
 
 // Activation1d(x) -> Conv1d fused (see conv_umma_fused_kernel).  Returns BVG_ERR_STATE without launching when the
@@ -489,13 +484,13 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   int n_nblk = 1;
   P.NPH = 1;
   umma_choose_nb(L.Cout, 1, &P.NB, &n_nblk);
-  if (n_nblk != 1 || P.NB > env_int("BVG_FUSE_MAX_NB", 128) || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
+  if (n_nblk != 1 || P.NB > BVG_ENV_ONCE("BVG_FUSE_MAX_NB", 128) || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
   P.ntaps = L.K;
   BVG_CHECK_ARG(L.K <= 16, "conv_umma_fused: at most 16 taps");
   // Wide-and-long layers (C = 96, k = 11) are bound by the number of narrow tcgen05.mma instructions (~100-150 cycles
   // each whatever N is) rather than by the stencil; in isolation the two-kernel path is faster there, inside the
   // decode the fused kernel still wins (one tensor pass less through HBM), so the cut-off is off by default.
-  if ((int64_t)((L.Cin + 15) / 16 * 16) * L.K > env_int("BVG_FUSE_MAX_CK", 1 << 30)) return BVG_ERR_STATE;
+  if ((int64_t)((L.Cin + 15) / 16 * 16) * L.K > BVG_ENV_ONCE("BVG_FUSE_MAX_CK", 1 << 30)) return BVG_ERR_STATE;
   const int halo = L.dil * (L.K - 1);
   P.lo = halo / 2;
   BVG_CHECK_ARG(P.lo <= x.pad, "conv_umma_fused: conv padding %d exceeds the c8t halo %d", P.lo, x.pad);
@@ -513,7 +508,9 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   P.bias = ep.bias; P.scale = ep.scale; P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
   P.act_alpha = act_alpha; P.act_beta = act_beta;
   P.dbg = ep.dbg;
-  P.dry = env_int("BVG_FUSE_DRY", 0);     // experiment: skip the stencil math (timing only, results are garbage)
+#ifdef BVG_DEBUG
+  P.dry = BVG_ENV_ONCE("BVG_FUSE_DRY", 0);     // debug builds only: skip the stencil math (timing experiments, results are garbage)
+#endif
   P.acc_stages = 2;
   P.n_nblk = 1;
   P.B = (int)B;
@@ -522,7 +519,9 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   // 512 rows and by two accumulator stages in TMEM.  BVG_FUSE_XR overrides for experiments.
   const int nwords = (std::min(L.Cin, kFBlk) + 1) / 2;
   int xr = std::min(512, std::max(1, kFLanes / nwords) * kFV);
-  if (const int e = env_int("BVG_FUSE_XR", 0)) xr = e / kFV * kFV;
+#ifdef BVG_DEBUG
+  if (const int e = BVG_ENV_ONCE("BVG_FUSE_XR", 0)) xr = e / kFV * kFV;   // debug builds only: untested tile geometries
+#endif
   auto nacc_of = [&](int rows) { return (rows - halo + 127) / 128; };
   // two accumulator stages (the epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 TMEM columns
   // at full stencil occupancy; wide layers (C = 192) keep the full tile and run with one stage instead
@@ -544,7 +543,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   if (2 * rsb + 2 * xsb + 2 * wsb > budget) return BVG_ERR_STATE;
   size_t used = 2 * rsb + 2 * xsb;
   bool resident = wslots <= kFMaxW && used + wslots * wsb <= budget;
-  if (env_int("BVG_FUSE_WRES", 1) == 0) resident = false;
+  if (BVG_ENV_ONCE("BVG_FUSE_WRES", 1) == 0) resident = false;
   if (resident) {
     P.w_resident = 1;
     P.w_stages = wslots;
@@ -556,8 +555,8 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   }
   used += P.w_stages * wsb;
   // leftover: deepen the A ring first (lets the stencil run ahead of the MMAs), then the raw ring
-  const int max_a = std::min(kFMaxA, std::max(2, env_int("BVG_FUSE_A", 3)));
-  const int max_raw = std::min(kFMaxRaw, std::max(2, env_int("BVG_FUSE_RAW", 3)));
+  const int max_a = std::min(kFMaxA, std::max(2, BVG_ENV_ONCE("BVG_FUSE_A", 3)));
+  const int max_raw = std::min(kFMaxRaw, std::max(2, BVG_ENV_ONCE("BVG_FUSE_RAW", 3)));
   P.a_stages = 2; P.x_stages = 2;
   for (bool grew = true; grew;) {
     grew = false;
@@ -566,19 +565,12 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
     if (P.acc_stages == 2 && P.a_stages < max_a && used + xsb <= budget) { ++P.a_stages; used += xsb; grew = true; }
   }
   const size_t smem = used + fused_fixed_smem(P.NB, P.Cin_p);
-  static bool attr_set = false;
-  if (!attr_set) {
-    BVG_CUDA(cudaFuncSetAttribute(conv_umma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  BVG_TRY(smem_opt_in(conv_umma_fused_kernel, opted, 227 * 1024));
   const int64_t ntiles = (int64_t)P.tiles_per_batch * B;
   BVG_CHECK_ARG(ntiles < (1ll << 31), "conv_umma_fused: too many tiles");
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    BVG_CUDA(cudaGetDevice(&dev));
-    BVG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  BVG_TRY(current_device_sms(&num_sms));
   dim3 grid((unsigned)std::min<int64_t>(ntiles, num_sms));
   ProfScope prof(st, KC_ACTCONV);
   conv_umma_fused_kernel<<<grid, kFThreads, smem, st>>>(P);

@@ -44,6 +44,24 @@ void prof_mark(cudaStream_t st, int kclass, bool begin) {
   }
 }
 
+int current_device_sms(int* sms) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  BVG_CUDA(cudaGetDevice(&dev));
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    BVG_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return BVG_OK;
+}
+
+int env_int_once(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 void set_error(const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -622,8 +640,12 @@ static long long* g_umma_dbg = nullptr;   // set by bvg_debug_set_umma_counters 
 static int g_umma_dry = 0;
 void bvg_debug_set_umma_counters(long long* dev_buf) {
   g_umma_dbg = dev_buf;
-  const char* e = getenv("BVG_UMMA_DRY");          // profiling only: issue-loop-only dry run (results are garbage)
+#ifdef BVG_DEBUG
+  const char* e = getenv("BVG_UMMA_DRY");          // debug builds only: issue-loop-only dry run (results are garbage)
   g_umma_dry = (dev_buf && e && e[0] == '1') ? 1 : 0;
+#else
+  g_umma_dry = 0;
+#endif
 }
 
 static int umma_layer_test(void* dst, const void* src, const float* weight, const float* bias, const void* res1,
@@ -663,7 +685,13 @@ static int umma_layer_test(void* dst, const void* src, const float* weight, cons
 
 int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log, int64_t B,
                       int64_t Cn, int64_t T, void* stream) {
+  return bvg_act1d_c8t_impl_fwd(dst, src, alpha_log, beta_log, B, Cn, T, 0, stream);
+}
+
+int bvg_act1d_c8t_impl_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log, int64_t B,
+                           int64_t Cn, int64_t T, int impl, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(impl >= 0 && impl <= 2, "act1d_c8t: impl must be 0, 1 or 2");
   BVG_CHECK_ARG(dst && src && alpha_log && beta_log && B >= 1 && Cn >= 1 && T >= 1, "act1d_c8t: bad argument");
   const size_t nb = c8t_bytes(B, (int)Cn, T);
   char* tmp = nullptr;
@@ -674,7 +702,7 @@ int bvg_act1d_c8t_fwd(void* dst, const void* src, const float* alpha_log, const 
   if (cudaMemsetAsync(tmp, 0x7f, 2 * nb + 512, st) != cudaSuccess) rc = BVG_ERR_CUDA;
   if (rc == BVG_OK) rc = to_c8t_launch(x, src, Cn * T, T, 1, BVG_BF16, B, st);
   if (rc == BVG_OK && cudaMemsetAsync(x.p, 0x7f, (size_t)x.pad * 16, st) != cudaSuccess) rc = BVG_ERR_CUDA;
-  if (rc == BVG_OK) rc = act1d_c8t_launch(y, x, alpha_log, beta_log, B, st);
+  if (rc == BVG_OK) rc = act1d_c8t_launch(y, x, alpha_log, beta_log, B, st, impl);
   if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
   cudaFreeAsync(tmp, st);
   return rc;

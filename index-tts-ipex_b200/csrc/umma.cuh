@@ -100,8 +100,11 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
 // Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)
+// impl: 0 = tensor-core FIRs when the tensor qualifies, else the CUDA-core stencil; 1 = stencil; 2 = tensor cores or error
 int act1d_c8t_launch(const C8T& y, const C8T& x, const float* alpha_log, const float* beta_log, int64_t B,
-                     cudaStream_t st);
+                     cudaStream_t st, int impl = 0);
+// the same on the tensor cores (act1d_tc.cu); BVG_ERR_STATE (nothing launched) if the tensor does not qualify
+int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const float* beta_log, int64_t B, cudaStream_t st);
 // conv_post (Cin->1) + tanh on a c8t tensor whose halo rows are zero; w is [Cin][K] fp32
 int conv_post_c8t_launch(float* wav, int16_t* pcm, const C8T& x, const float* w, const float* bias, int K,
                          int64_t s_lo, int64_t s_hi, int64_t B, cudaStream_t st);

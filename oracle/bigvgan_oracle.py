@@ -124,9 +124,11 @@ def act1d_taps() -> np.ndarray:
 # filter.py:87-96, activations.py:109-122)
 # --------------------------------------------------------------------------------------
 def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, taps=None,
-          logscale: bool = True) -> torch.Tensor:
+          logscale: bool = True, mid_dtype=None) -> torch.Tensor:
     """x [B,C,T] -> [B,C,T].  2x kaiser-sinc upsample (replicate pad 5/5, x ratio) ->
-    SnakeBeta -> 12-tap stride-2 lowpass (replicate pad 5/6 of the ACTIVATED signal)."""
+    SnakeBeta -> 12-tap stride-2 lowpass (replicate pad 5/6 of the ACTIVATED signal).
+    `mid_dtype` (tests only) rounds the activated 2x signal to that dtype before the down filter: the model of a
+    kernel that keeps this intermediate in reduced precision."""
     B, C, T = x.shape
     f = torch.as_tensor(act1d_taps() if taps is None else np.asarray(taps, dtype=np.float64),
                         dtype=x.dtype, device=x.device)
@@ -149,6 +151,8 @@ def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, taps=None,
         a_ = torch.exp(a_)
         b_ = torch.exp(b_)
     u = u + (1.0 / (b_ + 1e-9)) * torch.sin(u * a_) ** 2
+    if mid_dtype is not None:
+        u = u.to(mid_dtype).to(x.dtype)
     # --- DownSample1d (filter.py:87-96): replicate pad 5 left / 6 right, stride 2
     idx2 = torch.arange(-5, 2 * T + 6, device=x.device).clamp_(0, 2 * T - 1)
     ap = u[..., idx2]                                  # [B,C,2T+11]

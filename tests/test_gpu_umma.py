@@ -81,12 +81,12 @@ def test_act1d_c8t_vs_oracle(P, Cn, T):
     ref = O.act1d(x.double(), a.double(), b.double())
     y = torch.empty(2, Cn, T, device="cuda", dtype=torch.bfloat16)
     xd, ad, bd = x.cuda(), a.cuda(), b.cuda()
-    P.capi.check(P.capi.lib().bvg_act1d_c8t_fwd(y.data_ptr(), xd.data_ptr(), ad.data_ptr(), bd.data_ptr(), 2, Cn, T,
-                                                torch.cuda.current_stream().cuda_stream), "bvg_act1d_c8t_fwd")
+    P.capi.check(P.capi.lib().bvg_act1d_c8t_impl_fwd(y.data_ptr(), xd.data_ptr(), ad.data_ptr(), bd.data_ptr(), 2, Cn, T,
+                                                     1, torch.cuda.current_stream().cuda_stream), "bvg_act1d_c8t_impl_fwd")
     torch.cuda.synchronize()
     err = (y.double().cpu() - ref).abs()
     assert float((err - (ref.abs() * 2.0 ** -8 + 1e-4)).max()) <= 0, float(err.max())
-    # and it agrees with the plain-layout kernel to the last bit of the bf16 output
+    # and it (the CUDA-core stencil, impl = 1) agrees with the plain-layout kernel to the last bit of the bf16 output
     y2 = P.anti_alias_activation_forward(xd, None, None, ad, bd)
     assert torch.equal(y, y2)
 
@@ -112,7 +112,7 @@ def test_fused_actconv_equals_unfused(P, Cin, Cout, T, K, dil, monkeypatch):
     L = P.capi.lib()
     st = torch.cuda.current_stream().cuda_stream
     act = torch.empty_like(x)
-    P.capi.check(L.bvg_act1d_c8t_fwd(act.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), B, Cin, T, st))
+    P.capi.check(L.bvg_act1d_c8t_impl_fwd(act.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), B, Cin, T, 1, st))
     y_ref = torch.empty(B, Cout, T, device="cuda", dtype=torch.bfloat16)
     P.capi.check(L.bvg_conv1d_umma_fwd(y_ref.data_ptr(), act.data_ptr(), w.data_ptr(), bias.data_ptr(), r1.data_ptr(), None,
                                        0.5, B, Cin, Cout, T, K, dil, st))
