@@ -20,6 +20,12 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("BVG_DEBUG_BUILD") == "1":      # experiments only: enables the result-corrupting dry-run switches
+    NVCC_FLAGS = NVCC_FLAGS + ["-DBVG_DEBUG"]
+if os.environ.get("BVG_EXTRA_NVCC"):              # experiments only: extra -D switches (tile geometry sweeps)
+    NVCC_FLAGS = NVCC_FLAGS + os.environ["BVG_EXTRA_NVCC"].split()
+
+
 def lib_path() -> str:
     return os.path.join(LIBDIR, LIBNAME)
 
@@ -36,6 +42,7 @@ def _src_hash() -> str:
     h = hashlib.sha256()
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
         os.path.join(os.path.dirname(HERE), "include", "bigvgan_b200.h"), os.path.abspath(__file__)]
+    h.update(" ".join(NVCC_FLAGS).encode())
     for f in files:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())

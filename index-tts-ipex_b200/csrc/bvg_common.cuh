@@ -14,6 +14,7 @@ namespace bvg {
 
 void set_error(const char* fmt, ...);
 extern thread_local int64_t g_launches;
+extern long long* g_dbg_buf;      // optional per-role cycle counters (bvg_debug_set_umma_counters), else null
 
 // ---- optional per-kernel-class timing (bvg_profile_*): CUDA events around every launch ---------
 enum KernelClass { KC_ACT1D = 0, KC_CONV = 1, KC_CONVTR = 2, KC_OTHER = 3, KC_ACTCONV = 4, KC_COUNT = 5 };

@@ -475,8 +475,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
 // Activation1d(x) -> Conv1d fused (see conv_umma_fused_kernel).  Returns BVG_ERR_STATE without launching when the
 // layer does not qualify (caller falls back to act1d_c8t_launch + conv_umma_launch).
 int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,
-                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st) {
+                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st, int max_nb) {
   if (L.transposed || !act_alpha || !act_beta) return BVG_ERR_STATE;
+  if (max_nb <= 0) max_nb = BVG_ENV_ONCE("BVG_FUSE_MAX_NB", 128);
   BVG_CHECK_ARG(L.w && x.p && y.p, "conv_umma_fused: null pointer");
   BVG_CHECK_ARG(x.C == L.Cin && y.C == L.Cout && y.T == x.T, "conv_umma_fused: shape mismatch");
   UmmaConvParams P;
@@ -484,7 +485,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   int n_nblk = 1;
   P.NPH = 1;
   umma_choose_nb(L.Cout, 1, &P.NB, &n_nblk);
-  if (n_nblk != 1 || P.NB > BVG_ENV_ONCE("BVG_FUSE_MAX_NB", 128) || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
+  if (n_nblk != 1 || P.NB > max_nb || ep.cond || ep.relu || ep.post_scale || ep.act) return BVG_ERR_STATE;
   P.ntaps = L.K;
   BVG_CHECK_ARG(L.K <= 16, "conv_umma_fused: at most 16 taps");
   // Wide-and-long layers (C = 96, k = 11) are bound by the number of narrow tcgen05.mma instructions (~100-150 cycles

@@ -21,6 +21,7 @@ namespace bvg {
 
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
+long long* g_dbg_buf = nullptr;
 
 // profiler state (per calling thread)
 struct ProfRec { int kc; cudaEvent_t a, b; };
@@ -640,6 +641,7 @@ static long long* g_umma_dbg = nullptr;   // set by bvg_debug_set_umma_counters 
 static int g_umma_dry = 0;
 void bvg_debug_set_umma_counters(long long* dev_buf) {
   g_umma_dbg = dev_buf;
+  bvg::g_dbg_buf = dev_buf;
 #ifdef BVG_DEBUG
   const char* e = getenv("BVG_UMMA_DRY");          // debug builds only: issue-loop-only dry run (results are garbage)
   g_umma_dry = (dev_buf && e && e[0] == '1') ? 1 : 0;
@@ -734,7 +736,7 @@ int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, con
     UmmaEpilogue ep;
     ep.bias = bias; ep.scale = scale; ep.res1 = res1 ? r1.p : nullptr;
     ep.dbg = g_umma_dbg;
-    rc = conv_umma_fused_launch(L, x, alpha_log, beta_log, y, ep, B, st);
+    rc = conv_umma_fused_launch(L, x, alpha_log, beta_log, y, ep, B, st, /*max_nb=*/256);   // (the decode path stops at 128)
     if (rc == BVG_ERR_STATE) set_error("actconv: this layer shape does not qualify for the fused kernel");
   }
   if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);

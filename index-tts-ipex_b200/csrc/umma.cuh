@@ -95,8 +95,9 @@ int umma_pack_split_launch(__nv_bfloat16* dst, const float* src_torch_layout, in
 int split_to_c8t_launch(const C8T& dst, const float* src, int64_t sb, int64_t sc, int64_t st_, int C, int64_t B, cudaStream_t st);
 int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
 // Activation1d -> Conv1d in one kernel for narrow layers; BVG_ERR_STATE (nothing launched) if the layer does not qualify
+// max_nb: widest output-channel block accepted (0: the decode path's default, 128 unless BVG_FUSE_MAX_NB says otherwise)
 int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,
-                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st);
+                           const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st, int max_nb = 0);
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
 // Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)
