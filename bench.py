@@ -30,10 +30,11 @@ AUDIO_S_PER_UTT = T0 * UP / SR
 
 
 def workload_config(batch, precision, world):
-    """The `config` object both arms print (same workload; the reference arm runs a bounded sample of it)."""
+    """The `config` object of the GPU arm."""
     return {"workload": f"IndexTTS-1.5 BigVGAN decode (random init), {batch} x 10 s utterances per GPU "
-                        f"(T0={T0} latent frames, Tm={TM} mel frames), {precision} storage, utterance-sharded; "
-                        f"N>1 adds one NCCL all_gather of the fp32 waveforms per step",
+                        f"(T0={T0} latent frames, Tm={TM} mel frames), {precision} storage, utterance-sharded, output = "
+                        f"int16 PCM (the caller's clamp/int16 epilogue of infer.py:206-212,234 fused into conv_post); "
+                        f"N>1 adds one NCCL all_gather of the int16 waveforms per step",
             "global_batch": world * batch, "audio_s_per_step": world * batch * AUDIO_S_PER_UTT,
             "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -48,11 +49,19 @@ def peaks():
 
 
 FUSED_MAX_C = 128      # AMPBlock1 act->conv pairs with C <= 128 run as one fused kernel (conv_umma_fused.cu)
-# dram__bytes_read.sum + dram__bytes_write.sum per fused launch, averaged over the 54 fused launches of one benchmark
-# step (ncu capture of tools/prof_decode.py; see the named file)
-FUSED_TRAFFIC_PER_LAUNCH = 959.7e6
-FUSED_TRAFFIC_NOTE = ("profiles/r01_fused_dram_v7.csv: ncu dram__bytes_read.sum + dram__bytes_write.sum of the 54 fused "
-                      "launches of one step (B = 32 x 10 s): 51.82 GB in total = 959.7 MB per launch")
+
+
+def measured_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu capture of THIS
+    build committed under profiles/ (tools/traffic_from_ncu.py writes profiles/traffic.json next to the csv it read);
+    (None, note) when no capture of the current library exists -- never a number typed in by hand."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(path))
+        e = d[kernel_class]
+        return float(e["bytes_per_launch"]), f"{e['source']} ({e['launches']} launches, library {d.get('library', '?')})"
+    except Exception:
+        return None, "no ncu dram__bytes capture of this build under profiles/ (profiles/traffic.json)"
 
 
 def algorithmic_work(h, B, T0_, es=2, fused=True):
@@ -135,6 +144,83 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def act1d_sweep(pkg, torch, dev, pk):
+    """BASELINE config 5b, bounded: standalone Activation1d through the op boundary (plain [B,C,T] tensors,
+    `anti_alias_activation_cuda.forward` seam) on 3 shapes x {fp32, bf16} x {precise (libdevice sinf, the fp32 default),
+    fast (MUFU)}, in+out >= 512 MB per call (>> 126 MB L2); plus the decode path's own c8t bf16 kernels (CUDA-core
+    stencil and tensor-core FIRs) on the generator's stage shapes.  GB/s = 2*B*C*T*sizeof / CUDA-event time."""
+    out = {"op_boundary": [], "c8t_bf16": []}
+    L = pkg.capi.lib()
+
+    def timed(fn, iters=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for Cn, T, Bn in ((768, 4096, 44), (96, 65536, 22), (24, 1048576, 6)):
+        a = torch.randn(Cn, device=dev) * 0.5
+        b = torch.randn(Cn, device=dev) * 0.5
+        for dt, name, es in ((torch.float32, "fp32", 4), (torch.bfloat16, "bf16", 2)):
+            x = torch.randn(Bn, Cn, T, device=dev).to(dt)
+            for precise in (True, False):
+                ms = timed(lambda: pkg.anti_alias_activation_forward(x, None, None, a, b, precise=precise))
+                gbs = 2.0 * Bn * Cn * T * es / (ms * 1e-3) / 1e9
+                out["op_boundary"].append({"C": Cn, "T": T, "B": Bn, "dtype": name, "precise": precise, "ms": ms,
+                                           "GBps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
+            del x
+    st = torch.cuda.current_stream().cuda_stream
+    for Cn, T, Bn in ((768, 940, 32), (384, 3760, 32), (192, 15040, 32), (96, 60160, 32), (24, 240640, 32)):
+        x = (torch.randn(Bn, Cn, T, device=dev) * 1.5).to(torch.bfloat16)
+        y = torch.empty_like(x)
+        a = torch.randn(Cn, device=dev) * 0.5
+        b = torch.randn(Cn, device=dev) * 0.5
+        for impl, name in ((1, "cuda_core_stencil"), (2, "tensor_core_fir")):
+            for _ in range(2):
+                pkg.capi.check(L.bvg_act1d_c8t_impl_fwd(y.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), Bn, Cn, T, impl, st))
+            torch.cuda.synchronize()
+            pkg.capi.profile_begin()                    # (the entry point converts plain <-> c8t around the kernel: time the
+            for _ in range(5):                          #  Activation1d kernel class only)
+                pkg.capi.check(L.bvg_act1d_c8t_impl_fwd(y.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), Bn, Cn, T, impl, st))
+            ms = pkg.capi.profile_end()["act1d"][0] / 5
+            gbs = 4.0 * Bn * Cn * T / (ms * 1e-3) / 1e9
+            out["c8t_bf16"].append({"C": Cn, "T": T, "B": Bn, "impl": name, "ms": ms, "GBps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
+        del x, y
+    return out
+
+
+def latency_b1(m, O, h, torch, dev):
+    """BASELINE config 2: one 10 s utterance (B = 1, T0 = 235), ms per decode for the three precisions (CUDA events)."""
+    lat, mel = O.synthetic_inputs(h, 1, T0, TM, seed=3)
+    lat, mel = lat.to(dev), mel.to(dev)
+    res = {}
+    keep = m.precision
+    try:
+        for prec in ("fp32", "fp32x3", "bf16"):
+            m.precision = prec
+            for _ in range(2):
+                m.decode(lat, mel_ref=mel)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 3 if prec == "fp32" else 10
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                m.decode(lat, mel_ref=mel)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            res[prec] = {"ms": ms, "x_realtime": AUDIO_S_PER_UTT * 1e3 / ms}
+    finally:
+        m.precision = keep
+    return res
+
+
 def cpu_reference_rate(frames, threads=None, warm_frames=16):
     """audio-s/s of the oracle port (the reference's algorithm in torch fp32 on the host cores)."""
     import torch
@@ -186,9 +272,12 @@ def run_reference(args):
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, args.precision, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
-        "reference_note": "the reference's algorithm (oracle port, torch fp32) on the host CPU; each step is a bounded "
-                          "sample of the workload",
+        "config": {"workload": f"IndexTTS-1.5 BigVGAN decode (random init), CPU oracle port (kind: port), fp32, "
+                               f"1 utterance x {frames} latent frames (Tm={TM}) per step on {torch.get_num_threads()} host "
+                               f"threads: a bounded sample of the GPU arm's workload ({args.batch} x 10 s utterances per GPU)",
+                   "global_batch": 1, "audio_s_per_step": frames * UP / SR},
+        "reference_note": "the reference's algorithm (oracle port, torch fp32) on the host CPU; NOT the same batch as the "
+                          "GPU arm: audio-s/s is a rate, so the bounded sample stands for the workload",
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -223,12 +312,15 @@ def run_ours(args):
     lat_h, mel_h = lat_h.pin_memory(), mel_h.pin_memory()
     lat, mel = lat_h.to(dev), mel_h.to(dev)
     L = T0 * UP
-    gathered = torch.empty(world, B, 1, L, device=dev) if world > 1 else None
+    gathered = torch.empty(world * B, L, dtype=torch.int16, device=dev) if world > 1 else None
+    m._ensure_plan(dev)
+    ws = torch.empty(m.workspace_bytes(B, T0, TM), dtype=torch.uint8, device=dev)      # reused across steps
 
     def step():
-        wav = m.decode(lat, mel_ref=mel)
+        # int16 PCM out of the decode (fused caller epilogue); the bytes travel as uint8 (NCCL has no int16 datatype)
+        wav = m.decode(lat, mel_ref=mel, pcm16=True, workspace=ws)
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(world * B, 1, L), wav)
+            dist.all_gather_into_tensor(gathered.view(torch.uint8), wav.view(torch.uint8))
         return wav
 
     def barrier():
@@ -261,14 +353,14 @@ def run_ours(args):
     value = world * B * AUDIO_S_PER_UTT * args.steps / (total_ms / 1e3)
 
     # ---- end to end through the public host-buffer API: pinned H2D + decode + D2H every step
-    out_h = torch.empty(B, 1, L, dtype=torch.float32, pin_memory=True)     # reused result buffer, like the inputs
+    out_h = torch.empty(B, L, dtype=torch.int16, pin_memory=True)          # reused result buffer, like the inputs
     for _ in range(2):
-        m.decode_host(lat_h, mel_h, dev, out=out_h)
+        m.decode_host(lat_h, mel_h, dev, pcm16=True, out=out_h)
     barrier()
     t = time.perf_counter()
     n_e2e = max(2, min(args.steps, 5))
     for _ in range(n_e2e):
-        m.decode_host(lat_h, mel_h, dev, out=out_h)       # synchronises the stream before returning
+        m.decode_host(lat_h, mel_h, dev, pcm16=True, out=out_h)       # synchronises the stream before returning
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([(time.perf_counter() - t) * 1e3], device=dev)
     if world > 1:
@@ -282,7 +374,7 @@ def run_ours(args):
     pkg.capi.profile_begin()
     n_prof = 2
     for _ in range(n_prof):
-        m.decode(lat, mel_ref=mel)
+        m.decode(lat, mel_ref=mel, pcm16=True)
     prof = pkg.capi.profile_end()
     if rank == 0:
         es = 2 if args.precision == "bf16" else 4
@@ -304,8 +396,8 @@ def run_ours(args):
             # algorithmic bytes per launch / average launch time; traffic = ncu dram bytes per launch (same step)
             roof = {"kernel": "conv_umma_fused_kernel (Activation1d -> Conv1d, narrow stages)", "bound": "hbm",
                     "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": fus_gbs / pk["hbm"],
-                    "traffic": FUSED_TRAFFIC_PER_LAUNCH, "algorithmic_bytes_per_launch": work["fused_bytes"] / max(fus_n, 1),
-                    "traffic_note": FUSED_TRAFFIC_NOTE,
+                    "traffic": measured_traffic("actconv")[0], "algorithmic_bytes_per_launch": work["fused_bytes"] / max(fus_n, 1),
+                    "traffic_note": measured_traffic("actconv")[1],
                     "limiter": "FMA pipe (the 12+12-tap FIR stencil), not HBM: see profiles/README.md"}
         elif dom == "act1d":
             roof = {"kernel": "act1d_c8t_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
@@ -319,6 +411,12 @@ def run_ours(args):
         roof["launches_per_step"] = per_step[dom][1]
         roof["avg_launch_ms"] = per_step[dom][0] / max(per_step[dom][1], 1)
         roof["share_of_step_kernel_time"] = per_step[dom][0] / kernel_ms if kernel_ms else None
+        extras = None
+        if not args.no_extras and world == 1:
+            ex_sampler = ClockSampler(local)
+            ex_sampler.start()
+            extras = {"latency_b1_10s": latency_b1(m, O, h, torch, dev), "act1d_sweep": act1d_sweep(pkg, torch, dev, pk)}
+            extras["clocks"] = ex_sampler.stop()
         cpu_val, cpu_dt, cores = cpu_reference_rate(args.cpu_frames)
         line = {
             "metric": "bigvgan_decode_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
@@ -344,6 +442,7 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_val, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": f"1 utterance x {args.cpu_frames} latent frames "
                                        f"({args.cpu_frames * UP / SR:.2f} s audio), fp32 oracle port, {cpu_dt:.1f} s"},
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -360,6 +459,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default: the benchmark's 32)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32x3"])
     ap.add_argument("--cpu-frames", type=int, default=200, help="latent frames of the CPU-baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the B = 1 latencies and the Activation1d sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -13,14 +13,23 @@ import torch.nn as nn
 from . import capi
 
 
+# Filter buffers already validated against the compiled-in kaiser-sinc taps, keyed by (storage pointer, version): the
+# check needs the values on the host (one blocking D2H copy), so it runs once per buffer, not once per call -- a
+# generator pass makes ~100 Activation1d calls, and a per-call copy would serialise the stream and break graph capture.
+_validated_taps = set()
+
+
 def _taps_ptr(t):
+    """-> ctypes float[12] to validate, or None when `t` is absent or was validated before."""
     if t is None:
+        return None
+    key = (t.data_ptr(), t._version, t.device)
+    if key in _validated_taps:
         return None
     host = t.detach().reshape(-1).to("cpu", torch.float32).contiguous()
     if host.numel() != 12:
         raise RuntimeError("anti_alias_activation: the fused kernel hard-codes filter size 12 / ratio 2")
-    arr = (C.c_float * 12)(*host.tolist())
-    return arr
+    return (C.c_float * 12)(*host.tolist())
 
 
 def forward(inputs: torch.Tensor, up_ftr, down_ftr, alpha: torch.Tensor, beta: torch.Tensor,
@@ -47,6 +56,9 @@ def forward(inputs: torch.Tensor, up_ftr, down_ftr, alpha: torch.Tensor, beta: t
         capi.check(capi.lib().bvg_act1d_fwd(out.data_ptr(), x.data_ptr(), a.data_ptr(), b.data_ptr(), up, down,
                                             B, Cn, T, capi.dtype_code(x.dtype), int(bool(precise)), st),
                    "bvg_act1d_fwd")
+    for t in (up_ftr, down_ftr):          # the library accepted them: remember, so later calls skip the host copy
+        if t is not None:
+            _validated_taps.add((t.data_ptr(), t._version, t.device))
     return out
 
 

@@ -43,7 +43,8 @@ def _schema(h):
 
     def act(p, c):
         out.append((p + ".act.alpha", (c,), "alpha", 0))
-        out.append((p + ".act.beta", (c,), "alpha", 0))
+        if h.activation != "snake":                      # Snake has alpha only (activations.py:25-47)
+            out.append((p + ".act.beta", (c,), "alpha", 0))
         out.append((p + ".upsample.filter", (1, 1, 12), "filt", 0))
         out.append((p + ".downsample.lowpass.filter", (1, 1, 12), "filt", 0))
 
@@ -137,8 +138,8 @@ class BigVGAN(nn.Module):
         if h.activation not in ("snakebeta", "snake"):
             raise NotImplementedError(
                 "activation incorrectly specified. check the config file and look for 'activation'.")  # models.py:63,182
-        if h.activation == "snake":
-            raise NotImplementedError("Snake (alpha == beta) checkpoints: load as SnakeBeta with beta := alpha")
+        # Snake (activations.py:49-60) is SnakeBeta with beta := alpha; its modules carry no `beta` parameter
+        self.snake_only = h.activation == "snake"
         if h.feat_upsample:
             raise NotImplementedError("feat_upsample=True is not used by IndexTTS (models.py:213-218)")
         self.num_kernels = len(h.resblock_kernel_sizes)
@@ -179,8 +180,8 @@ class BigVGAN(nn.Module):
             elif kind == "bcount":
                 _attach(self, key, torch.zeros((), dtype=torch.long), True)
         del pending_g
-        self._plan = None
-        self._plan_device = None
+        self._plans = {}                 # device index -> bvg_plan*; one plan per device, built on first use
+        self._plan_gen = 0               # bumped whenever the weights may have changed: captured CUDA graphs go stale
         self._plan_lock = threading.Lock()
         # None: fp32, or bf16 under torch.autocast; "fp32" / "bf16" to force; "fp32x3": fp32 tensors with the Conv1d
         # layers on the tensor cores (3-term bf16 split, ~2e-6 max-abs against the fp32 path's 5e-7)
@@ -188,10 +189,22 @@ class BigVGAN(nn.Module):
 
     # ------------------------------------------------------------------ module plumbing
     def _invalidate(self):
-        if getattr(self, "_plan", None) is not None:
-            capi.lib().bvg_plan_destroy(self._plan)
-        self._plan = None
-        self._plan_device = None
+        """Weights (may) have changed: drop every device's plan.  CUDA graphs captured by make_graphed_decode hold raw
+        pointers into a plan, so they are marked stale (their run() raises) instead of replaying freed memory."""
+        plans = getattr(self, "_plans", None)
+        if plans:
+            for plan in plans.values():
+                capi.lib().bvg_plan_destroy(plan)
+            plans.clear()
+        self._plan_gen = getattr(self, "_plan_gen", 0) + 1
+
+    @staticmethod
+    def _device_index(device) -> int:
+        """torch.device('cuda') and torch.device('cuda:0') name the same device: plans are keyed by the index."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("BigVGAN (B200): inputs must live on a CUDA device; there is no CPU path")
+        return device.index if device.index is not None else torch.cuda.current_device()
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
@@ -235,16 +248,18 @@ class BigVGAN(nn.Module):
                 yield k[:-2], (v * (g / nrm)).float()
             else:
                 yield k, v.float()
+                if self.snake_only and k.endswith(".act.alpha"):
+                    yield k[:-5] + "beta", v.float()
 
-    def _ensure_plan(self, device: torch.device):
-        if self._plan is not None and self._plan_device == device:
-            return self._plan
+    def _ensure_plan(self, device):
+        idx = self._device_index(device)          # validates the device BEFORE anything is torn down
+        plan = self._plans.get(idx)
+        if plan is not None:
+            return plan
         with self._plan_lock:
-            if self._plan is not None and self._plan_device == device:
-                return self._plan
-            self._invalidate()
-            if device.type != "cuda":
-                raise RuntimeError("BigVGAN (B200): inputs must live on a CUDA device; there is no CPU path")
+            plan = self._plans.get(idx)
+            if plan is not None:
+                return plan
             h = self.h
             cfg = capi.BvgConfig()
             cfg.gpt_dim = int(h.gpt_dim)
@@ -262,7 +277,7 @@ class BigVGAN(nn.Module):
             cfg.num_mels = int(h.num_mels)
             cfg.cond_in_each_up_layer = int(self.cond_in_each_up_layer)
             cfg.snake_logscale = int(bool(h.snake_logscale))
-            cfg.device = device.index if device.index is not None else torch.cuda.current_device()
+            cfg.device = idx
             L = capi.lib()
             plan = C.c_void_p()
             capi.check(L.bvg_plan_create(C.byref(plan), C.byref(cfg)), "bvg_plan_create")
@@ -274,8 +289,7 @@ class BigVGAN(nn.Module):
             except Exception:
                 L.bvg_plan_destroy(plan)
                 raise
-            self._plan = plan
-            self._plan_device = device
+            self._plans[idx] = plan
             return plan
 
     # ------------------------------------------------------------------ compute
@@ -288,9 +302,9 @@ class BigVGAN(nn.Module):
         return {"fp32": capi.BVG_F32, "bf16": capi.BVG_BF16, "fp32x3": capi.BVG_F32X3}[p]
 
     def workspace_bytes(self, B, T0, Tm, dtype_code=None):
-        plan = self._plan
-        if plan is None:
+        if not self._plans:
             raise RuntimeError("plan not built yet; call the model once or _ensure_plan(device)")
+        plan = next(iter(self._plans.values()))      # sizes depend on the config only, not on the device
         return int(capi.lib().bvg_workspace_bytes(plan, B, T0, Tm, self._dtype_code() if dtype_code is None else dtype_code))
 
     @torch.no_grad()
@@ -423,7 +437,12 @@ class BigVGAN(nn.Module):
             with torch.cuda.graph(graph):
                 enqueue()
 
+        gen = self._plan_gen
+
         def run(latent, mel_ref):
+            if self._plan_gen != gen:
+                raise RuntimeError("graphed decode is stale: the model's weights / device changed after capture "
+                                   "(load_state_dict, .to(), remove_weight_norm); call make_graphed_decode again")
             lat.copy_(latent, non_blocking=True)
             mel.copy_(mel_ref, non_blocking=True)
             graph.replay()

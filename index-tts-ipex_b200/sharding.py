@@ -29,9 +29,10 @@ def decode_sharded(decode_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tenso
                    mel_ref: torch.Tensor, group: Optional["dist.ProcessGroup"] = None,
                    gather: bool = True) -> torch.Tensor:
     """Every rank passes the SAME full batch (latent [B,T0,D], mel_ref [B or 1,Tm,M]); each decodes its
-    shard with `decode_fn(latent_shard, mel_shard) -> wav [b,1,L]` and, when `gather`, all ranks
-    return the full [B,1,L] waveform tensor (one all_gather; ragged shards are padded to the largest
-    shard for the collective and trimmed afterwards)."""
+    shard with `decode_fn(latent_shard, mel_shard) -> wav [b,1,L]` (fp32) or `[b,L]` (int16 PCM, the fused
+    epilogue of infer.py:206-212,234: half the bytes on the wire) and, when `gather`, all ranks return the full
+    waveform tensor of that layout (one all_gather; ragged shards are padded to the largest shard for the
+    collective and trimmed afterwards)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = latent.shape[0]
@@ -51,11 +52,19 @@ def decode_sharded(decode_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tenso
     dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=group)
     L = int(meta.item())
     cap = max(h - l for l, h in bounds)
-    dtype = wav.dtype if wav is not None else torch.float32
-    buf = torch.zeros(cap, 1, L, dtype=dtype, device=dev)
+    # ranks with an empty shard learn the layout (dtype, rank of the tensor) from the others
+    lay = torch.tensor([0 if wav is None else (2 if wav.dtype == torch.int16 else 1)], dtype=torch.int64, device=dev)
+    dist.all_reduce(lay, op=dist.ReduceOp.MAX, group=group)
+    pcm = int(lay.item()) == 2
+    dtype = torch.int16 if pcm else torch.float32
+    shape = (L,) if pcm else (1, L)
+    buf = torch.zeros(cap, *shape, dtype=dtype, device=dev)
     if wav is not None:
         buf[: hi - lo] = wav
-    out = torch.empty(world * cap, 1, L, dtype=dtype, device=dev)
-    dist.all_gather_into_tensor(out, buf, group=group)
+    out = torch.empty(world * cap, *shape, dtype=dtype, device=dev)
+    if pcm:      # neither NCCL nor gloo has an int16 datatype: the PCM bytes travel as uint8
+        dist.all_gather_into_tensor(out.view(torch.uint8), buf.view(torch.uint8), group=group)
+    else:
+        dist.all_gather_into_tensor(out, buf, group=group)
     parts = [out[r * cap: r * cap + (h - l)] for r, (l, h) in enumerate(bounds)]
     return torch.cat(parts, dim=0)

@@ -248,7 +248,8 @@ def state_dict_schema(h):
 
     def act(p, c):
         out.append((p + ".act.alpha", (c,), "alpha"))
-        out.append((p + ".act.beta", (c,), "beta"))
+        if getattr(h, "activation", "snakebeta") != "snake":      # Snake has alpha only (activations.py:25-47)
+            out.append((p + ".act.beta", (c,), "beta"))
         out.append((p + ".upsample.filter", (1, 1, 12), "filt"))
         out.append((p + ".downsample.lowpass.filter", (1, 1, 12), "filt"))
 
@@ -283,11 +284,13 @@ def make_state_dict(h, seed: int = 0, mode: str = "tame") -> "OrderedDict[str, t
 
     mode "tame": the distributions the reference ctor produces with default init
                  (kaiming-uniform v, g = ||v||, alpha = beta = 0, BN identity stats).
+    mode "stress": "wild" with alpha ~ N(0, 1.5) and beta ~ N(0, 1) (large snake arguments).
     mode "wild": additionally randomises g (x U[0.7,1.3]), alpha/beta ~ N(0,0.5) and the BN
                  affine/running stats, so weight-norm folding, log-scale snake parameters
                  and BN folding are actually exercised (SURVEY.md §8(c) extra checks)."""
     g = torch.Generator().manual_seed(int(seed))
-    wild = mode == "wild"
+    stress = mode == "stress"          # "wild" with alpha ~ N(0, 1.5), beta ~ N(0, 1): snake arguments of hundreds of radians
+    wild = mode == "wild" or stress
     taps = torch.tensor(act1d_taps(), dtype=torch.float32).view(1, 1, 12)
     sd = OrderedDict()
     pending_v = None
@@ -308,7 +311,8 @@ def make_state_dict(h, seed: int = 0, mode: str = "tame") -> "OrderedDict[str, t
             sd[key] = None  # filled after v is known
             pending_v = key
         elif kind in ("alpha", "beta"):
-            sd[key] = torch.randn(shape, generator=g) * 0.5 if wild else torch.zeros(shape)
+            sd[key] = torch.randn(shape, generator=g) * ((1.5 if kind == "alpha" else 1.0) if stress else 0.5) if wild \
+                else torch.zeros(shape)
         elif kind == "filt":
             sd[key] = taps.clone()
         elif kind == "bn_w":
@@ -434,7 +438,9 @@ def ecapa_forward(mel: torch.Tensor, sd, prefix: str = "speaker_encoder.") -> to
 # --------------------------------------------------------------------------------------
 def _act(x, sd, p, h):
     taps = sd[p + ".upsample.filter"].reshape(-1).double().cpu().numpy()
-    return act1d(x, sd[p + ".act.alpha"], sd[p + ".act.beta"], taps, logscale=bool(h.snake_logscale))
+    # Snake (activations.py:49-60): x + 1/(alpha + 1e-9) sin^2(alpha x), i.e. SnakeBeta with beta := alpha
+    beta = sd[p + ".act.alpha"] if getattr(h, "activation", "snakebeta") == "snake" else sd[p + ".act.beta"]
+    return act1d(x, sd[p + ".act.alpha"], beta, taps, logscale=bool(h.snake_logscale))
 
 
 def amp_block1(x, sd, p, h, k, dils):

@@ -33,7 +33,7 @@ def _run(P, x, a, b, impl):
 # many ranges per utterance, B = 1 .. 3
 @pytest.mark.parametrize("Cn,T,B", [(24, 4097, 2), (48, 2040, 2), (96, 1000, 3), (192, 257, 2), (200, 520, 2), (384, 300, 1),
                                     (768, 940, 2), (24, 70001, 1), (96, 16389, 2), (8, 256, 1), (16, 999, 2), (40, 1283, 1),
-                                    (256, 3760, 1), (192, 15040, 1)])
+                                    (256, 3760, 1), (192, 15040, 1), (3, 2000, 2), (6, 20480, 2)])
 def test_act1d_tc_vs_oracle(P, Cn, T, B):
     gen = torch.Generator().manual_seed(Cn * 13 + T)
     x = (torch.randn(B, Cn, T, generator=gen) * 1.5).to(torch.bfloat16)

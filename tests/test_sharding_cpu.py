@@ -25,6 +25,11 @@ def _fake_decode(latent, mel):
     return base + torch.arange(L, dtype=latent.dtype).view(1, 1, L)
 
 
+def _fake_decode_pcm(latent, mel):
+    # the int16 PCM layout of the fused epilogue: [b, L]
+    return _fake_decode(latent, mel).squeeze(1).clamp(-3e4, 3e4).to(torch.int16)
+
+
 def _worker(rank, world, port, B, Bm, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,6 +48,10 @@ def _worker(rank, world, port, B, Bm, q):
     ok = out.shape == ref.shape and torch.equal(out, ref)
     lo, hi = P.shard_bounds(B, world)[rank]
     ok = ok and (calls == ([hi - lo] if hi > lo else []))
+    # int16 PCM shards travel as int16 (half the gather bytes), ranks with an empty shard included
+    out16 = P.decode_sharded(_fake_decode_pcm, latent, mel)
+    ref16 = _fake_decode_pcm(latent, mel)
+    ok = ok and out16.dtype == torch.int16 and out16.shape == ref16.shape and torch.equal(out16, ref16)
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
