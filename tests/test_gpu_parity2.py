@@ -52,24 +52,59 @@ def _oracle_gpu(latent, mel, sd, h):
 # ------------------------------------------------------------------ full size, randomised weights (weak 1)
 @pytest.mark.parametrize("mode", ["wild", "stress"])
 def test_full_size_10s_randomised_weights_all_precisions(P, mode):
-    """T0 = 235 on the IndexTTS-1.5 config with randomised alpha / beta / weight-norm g / BN statistics; "stress" draws
-    alpha ~ N(0, 1.5): snake arguments of hundreds of radians (the MUFU cosine's error grows with the argument)."""
+    """T0 = 235 on the IndexTTS-1.5 config with randomised alpha / beta / weight-norm g / BN statistics.
+    "wild" (alpha, beta ~ N(0, 0.5)) must hold the north_star gates as they stand.  "stress" draws alpha ~ N(0, 1.5):
+    snake arguments of hundreds of radians through ~110 layers make the network itself ill-conditioned -- the reference's
+    own fp32 arithmetic then differs from exact arithmetic by far more than 1e-4 -- so its gate is the reference's own
+    noise floor (fp32 oracle against the float64 oracle), not an absolute number."""
     m, sd, h = _model(P, "indextts15", 3, mode)
     latent, mel = O.synthetic_inputs(h, 1, 235, 281, seed=7)
     ref = _oracle_gpu(latent, mel, sd, h)
     assert float(ref.abs().max()) > 0.01
+    gate_abs, gate_snr = FP32_GATE, BF16_SNR_GATE
+    if mode == "stress":
+        sd64 = {k: v.double().cuda() for k, v in O.fold_weight_norm(sd).items()}
+        with torch.no_grad():
+            ref64 = O.bigvgan_forward(latent.double().cuda(), mel.double().cuda(), sd64, h)
+        floor = float((ref.double() - ref64).abs().max())
+        floor_snr = O.snr_db(ref64.float().cpu(), ref.cpu())
+        print(f"stress: fp32 reference vs float64: max-abs {floor:.3e}, SNR {floor_snr:.1f} dB")
+        gate_abs = max(FP32_GATE, 4.0 * floor)
+        gate_snr = min(BF16_SNR_GATE, floor_snr - 6.0)
+        ref = ref64.float()
     try:
         for prec, check in (("fp32", "abs"), ("fp32x3", "abs"), ("bf16", "snr")):
             m.precision = prec
             y = m.decode(latent.cuda(), mel_ref=mel.cuda())
+            assert torch.isfinite(y).all()
             if check == "abs":
                 err = float((y - ref).abs().max())
-                assert err <= FP32_GATE, (prec, mode, err)
+                assert err <= gate_abs, (prec, mode, err, gate_abs)
             else:
                 snr = O.snr_db(ref.cpu(), y.cpu())
-                assert snr >= BF16_SNR_GATE, (prec, mode, snr)
+                assert snr >= gate_snr, (prec, mode, snr, gate_snr)
     finally:
         m.precision = None
+
+
+@pytest.mark.parametrize("dtype,precise", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, False)])
+def test_act1d_op_large_alpha(P, dtype, precise):
+    """One Activation1d with alpha ~ N(0, 1.5) (cosine arguments up to several hundred radians): the layer itself is well
+    conditioned, so the kernels are held to what fp32 arithmetic allows: the argument z = e^alpha u carries half an fp32
+    ulp (2^-24 |z|, the reference's own torch.sin(x * alpha) has the same), the un-reduced MUFU cosine 1.3e-7 |z|
+    (profiles/r02_umma_probe4.txt), both times the snake amplitude 1/(e^beta); plus the output rounding."""
+    gen = torch.Generator().manual_seed(17)
+    Cn, T = 48, 3000
+    x = (torch.randn(2, Cn, T, generator=gen) * 2.0).to(dtype)
+    a = torch.randn(Cn, generator=gen) * 1.5
+    b = torch.randn(Cn, generator=gen) * 1.0
+    ref = O.act1d(x.double(), a.double(), b.double())
+    y = P.anti_alias_activation_forward(x.cuda(), None, None, a.cuda(), b.cuda(), precise=precise).double().cpu()
+    zmax = float(2.0 * a.exp().max() * 8.0)                         # |2 e^alpha u| bound for |u| <= 8
+    gain = float((0.5 / (b.exp() + 1e-9)).max())
+    eps = {torch.float32: 0.0, torch.bfloat16: 2.0 ** -8}[dtype]
+    tol = (2.0 ** -23 if precise else 3e-7) * zmax * gain + 2e-5
+    assert float(((y - ref).abs() - (ref.abs() * eps + tol)).max()) <= 0, float((y - ref).abs().max())
 
 
 # ------------------------------------------------------------------ every utterance of config 3 (weak 2)
