@@ -128,6 +128,13 @@ BVG_API void bvg_debug_set_umma_counters(long long* dev_buf);
 BVG_API int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
                          const float* weight, const float* bias, const void* res1, float scale,
                          int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);
+/* The same with a second residual and a choice of kernel: impl 0 = what the decode path runs (tensor-core FIR kernel
+ * actconv_tc.cu when the layer qualifies -- C = 24 / 48 / 96, T >= 512 -- else the CUDA-core stencil kernel), 1 = the
+ * CUDA-core stencil kernel (conv_umma_fused.cu), 2 = the tensor-core FIR kernel or status 3.  Also rewrites the output's
+ * zero halo rows (the decode path's zero_pads).  Test entry point (allocates temporaries). */
+BVG_API int bvg_actconv_impl_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                         const float* weight, const float* bias, const void* res1, const void* res2, float scale,
+                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, int impl, void* stream);
 BVG_API int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias,
                         const void* res1, const void* res2, float scale,
                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, void* stream);

@@ -387,6 +387,7 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
 
 struct GenWs {
   void *A, *Y, *T1, *T2, *XS;
+  void* edge;               // actconv_tc_launch scratch (exact edge rows of the fused activation)
   void* X3;                 // [hi | lo] c8t staging of one conv input (fp32x3 path)
   float* cond[9];
   float* spk;
@@ -407,6 +408,7 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
   }
   const size_t bytes = (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * es;
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
+  g->edge = b.take(actconv_tc_scratch_bytes(B));
   g->X3 = nullptr;
   if (dtype == BVG_F32X3) {
     size_t x3 = c8t_bytes(B, 2 * ((P->cfg.gpt_dim + 7) / 8 * 8), T0);
@@ -472,6 +474,19 @@ int gen_conv(void* dst, const void* src, const ConvLayer& L, ConvEpilogue ep, in
 // never exists in HBM); layers that do not qualify fall back to the Activation1d kernel + conv kernel.
 // BVG_FUSE=0 forces the two-kernel path everywhere (A/B measurements, tests).
 const bool g_fuse_act = [] { const char* e = getenv("BVG_FUSE"); return !(e && e[0] == '0'); }();
+// BVG_FUSE_TC=0 keeps the round-1 fused kernel (FIRs on the FP32 pipe) for every fused layer (A/B measurements)
+const bool g_fuse_tc = [] { const char* e = getenv("BVG_FUSE_TC"); return !(e && e[0] == '0'); }();
+
+// Activation1d -> Conv1d as one kernel: tensor-core FIRs when the layer qualifies, else the CUDA-core stencil version
+int fused_act_conv(const UmmaLayer& L, const C8T& x, const float* alpha, const float* beta, const C8T& y, const UmmaEpilogue& ep,
+                   int64_t B, void* scratch, cudaStream_t st) {
+  if (!g_fuse_act) return BVG_ERR_STATE;
+  if (g_fuse_tc) {
+    const int rc = actconv_tc_launch(L, x, alpha, beta, y, ep, B, scratch, st);
+    if (rc != BVG_ERR_STATE) return rc;
+  }
+  return conv_umma_fused_launch(L, x, alpha, beta, y, ep, B, st);
+}
 
 UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1) {
   UmmaLayer u;
@@ -516,8 +531,7 @@ int decode_bf16_umma(const bvg_plan* P, const float* latent, const GenWs& g, int
         // xt = c1(a1(x)): one fused kernel for narrow layers, Activation1d kernel + conv kernel otherwise
         UmmaEpilogue e1;
         e1.bias = R.c1[m].bias;
-        int rc = g_fuse_act ? conv_umma_fused_launch(ulayer(R.c1[m], R.dil[m]), *cur, R.alpha[2 * m], R.beta[2 * m], t2, e1, B, st)
-                            : BVG_ERR_STATE;
+        int rc = fused_act_conv(ulayer(R.c1[m], R.dil[m]), *cur, R.alpha[2 * m], R.beta[2 * m], t2, e1, B, g.edge, st);
         if (rc == BVG_ERR_STATE) {
           BVG_TRY(act1d_c8t_launch(t1, *cur, R.alpha[2 * m], R.beta[2 * m], B, st));
           rc = conv_umma_launch(ulayer(R.c1[m], R.dil[m]), t1, t2, e1, B, st);
@@ -534,8 +548,7 @@ int decode_bf16_umma(const bvg_plan* P, const float* latent, const GenWs& g, int
           e2.zero_pads = 1;
           out = &xs;
         }
-        rc = g_fuse_act ? conv_umma_fused_launch(ulayer(R.c2[m], 1), t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], *out, e2, B, st)
-                        : BVG_ERR_STATE;
+        rc = fused_act_conv(ulayer(R.c2[m], 1), t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], *out, e2, B, g.edge, st);
         if (rc == BVG_ERR_STATE) {
           BVG_TRY(act1d_c8t_launch(t1, t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, st));
           rc = conv_umma_launch(ulayer(R.c2[m], 1), t1, *out, e2, B, st);
@@ -710,38 +723,54 @@ int bvg_act1d_c8t_impl_fwd(void* dst, const void* src, const float* alpha_log, c
   return rc;
 }
 
-int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
-                         const float* weight, const float* bias, const void* res1, float scale, int64_t B, int64_t Cin,
-                         int64_t Cout, int64_t T, int K, int dilation, void* stream) {
+int bvg_actconv_impl_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                         const float* weight, const float* bias, const void* res1, const void* res2, float scale,
+                         int64_t B, int64_t Cin, int64_t Cout, int64_t T, int K, int dilation, int impl, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BVG_CHECK_ARG(dst && src && weight && alpha_log && beta_log && B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1, "actconv: bad argument");
+  BVG_CHECK_ARG(impl >= 0 && impl <= 2, "actconv: impl must be 0, 1 or 2");
   const size_t xb = c8t_bytes(B, (int)Cin, T), yb = c8t_bytes(B, (int)Cout, T);
   const size_t wb = (size_t)umma_pack_elems((int)Cout, (int)Cin, K, 1) * 2;
+  const size_t sb = actconv_tc_scratch_bytes(B);
   char* tmp = nullptr;
-  BVG_CUDA(cudaMallocAsync((void**)&tmp, xb + 2 * yb + wb + 1024, st));
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  BVG_CUDA(cudaMallocAsync((void**)&tmp, al(xb) + 3 * al(yb) + al(wb) + sb + 1024, st));
   C8T x = make_c8t(tmp, (int)Cin, (int)T);
   C8T y = make_c8t(tmp + al(xb), (int)Cout, (int)T);
   C8T r1 = make_c8t(tmp + al(xb) + al(yb), (int)Cout, (int)T);
-  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(tmp + al(xb) + 2 * al(yb));
+  C8T r2 = make_c8t(tmp + al(xb) + 2 * al(yb), (int)Cout, (int)T);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(tmp + al(xb) + 3 * al(yb));
+  void* scratch = tmp + al(xb) + 3 * al(yb) + al(wb);
   int rc = BVG_OK;
   if (cudaMemsetAsync(tmp, 0x7f, xb, st) != cudaSuccess) rc = BVG_ERR_CUDA;      // poison: halo rows must not matter
   if (rc == BVG_OK) rc = to_c8t_launch(x, src, Cin * T, T, 1, BVG_BF16, B, st);
   if (rc == BVG_OK && cudaMemsetAsync(x.p, 0x7f, (size_t)x.pad * 16, st) != cudaSuccess) rc = BVG_ERR_CUDA;
   if (rc == BVG_OK && res1) rc = to_c8t_launch(r1, res1, Cout * T, T, 1, BVG_BF16, B, st);
+  if (rc == BVG_OK && res2) rc = to_c8t_launch(r2, res2, Cout * T, T, 1, BVG_BF16, B, st);
   if (rc == BVG_OK) rc = umma_pack_launch(wp, weight, (int)Cout, (int)Cin, K, 0, 1, st);
   if (rc == BVG_OK) {
     UmmaLayer L;
     L.w = wp; L.Cin = (int)Cin; L.Cout = (int)Cout; L.K = K; L.dil = dilation;
     UmmaEpilogue ep;
-    ep.bias = bias; ep.scale = scale; ep.res1 = res1 ? r1.p : nullptr;
+    ep.bias = bias; ep.scale = scale; ep.res1 = res1 ? r1.p : nullptr; ep.res2 = res2 ? r2.p : nullptr;
+    ep.zero_pads = 1;
     ep.dbg = g_umma_dbg;
-    rc = conv_umma_fused_launch(L, x, alpha_log, beta_log, y, ep, B, st, /*max_nb=*/256);   // (the decode path stops at 128)
+    rc = BVG_ERR_STATE;
+    if (impl != 1) rc = actconv_tc_launch(L, x, alpha_log, beta_log, y, ep, B, scratch, st);
+    if (rc == BVG_ERR_STATE && impl != 2)
+      rc = conv_umma_fused_launch(L, x, alpha_log, beta_log, y, ep, B, st, /*max_nb=*/256);   // (the decode path stops at 128)
     if (rc == BVG_ERR_STATE) set_error("actconv: this layer shape does not qualify for the fused kernel");
   }
   if (rc == BVG_OK) rc = from_c8t_launch(dst, y, BVG_BF16, B, st);
   cudaFreeAsync(tmp, st);
   return rc;
+}
+
+int bvg_actconv_umma_fwd(void* dst, const void* src, const float* alpha_log, const float* beta_log,
+                         const float* weight, const float* bias, const void* res1, float scale, int64_t B, int64_t Cin,
+                         int64_t Cout, int64_t T, int K, int dilation, void* stream) {
+  return bvg_actconv_impl_fwd(dst, src, alpha_log, beta_log, weight, bias, res1, nullptr, scale, B, Cin, Cout, T, K, dilation, 1,
+                              stream);
 }
 
 int bvg_conv1d_umma_fwd(void* dst, const void* src, const float* weight, const float* bias, const void* res1,

@@ -98,6 +98,11 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
 // max_nb: widest output-channel block accepted (0: the decode path's default, 128 unless BVG_FUSE_MAX_NB says otherwise)
 int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta,
                            const C8T& y, const UmmaEpilogue& ep, int64_t B, cudaStream_t st, int max_nb = 0);
+// the same with both anti-alias FIRs on the tensor cores (actconv_tc.cu; C = 24 / 48 / 96).  `scratch` holds
+// actconv_tc_scratch_bytes(B) bytes (the exact edge rows of the activation); BVG_ERR_STATE if the layer does not qualify
+size_t actconv_tc_scratch_bytes(int64_t B);
+int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta, const C8T& y,
+                      const UmmaEpilogue& ep, int64_t B, void* scratch, cudaStream_t st);
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
 // Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)
