@@ -46,12 +46,13 @@ constexpr int kXR = kXB * kBlk + 16;             // rows per chunk of a staged i
 constexpr int kSlots = 12;                       // 8-channel chunk-slots = 96 TMEM lanes (the up-FIR's M = 128 reads 4 phantom slots)
 constexpr uint32_t kXStageBytes = (uint32_t)kSlots * kXR * 16u;
 constexpr int kMaxXS = 4, kMaxAS = 3, kMaxWS = 8;
-constexpr int kNU = 2, kNY = 2;                  // U / Y accumulator buffers
+constexpr int kMaxNU = 4, kMaxNY = 4;            // U / Y accumulator buffers (P.nu / P.ny of them)
 constexpr int kThreads = 1024;
 // warp roles: a warp reaches TMEM lanes 32 (w % 4) .. +31 only, so the 12 snake / 6 store warps are the w % 4 < 3 ones
 constexpr int kWProdX = 3, kWProdW = 7, kWUp = 11, kWDn = 15, kWConv = 19, kWPatch = 23;
 constexpr int kWStore0 = 16, kWEpi0 = 24;
-constexpr uint32_t kColU = 0, kColA = 128, kColY = 256, kColC = 320;   // TMEM columns: U 2x64 | A ring 4x32 | Y 2x32 | conv
+// TMEM columns (512): U nu x 64 | A ring 4 x 32 | Y ny x 32 | conv accumulators nacc x S x NB  (P.colA / colY / colC)
+constexpr uint32_t kColU = 0;
 constexpr uint32_t kAHi = 0x4000u | (uint32_t)kXR;                     // up-FIR A descriptor: SBO = chunk pitch, version bit
 constexpr uint32_t kUpBytes = 6u * 64u * 16u, kDnBytes = 12u * 32u * 16u;
 constexpr int kDumpBytes = 512;
@@ -66,10 +67,26 @@ struct ActConvTcParams {
   int C, rc, S, Cin_p, NB, Cout, K, dil, lo, LH, SR, NP;
   int T, RL, NG, nitems;
   int nxs, nas, nacc, w_resident, w_slots;
+  int nu, ny; uint32_t colA, colY, colC;
+  int pace;                           // conv MMAs per pacing group (two groups in flight at most)
   uint32_t w_slot_bytes, w_total_bytes, a_stage_bytes;
   int zero_pads;
   long long* dbg;
+  long long* trace;
+  int dry;                            // BVG_DEBUG builds only (BVG_TCF_DRY): skip parts of the pipeline, results are garbage
 };
+#ifdef BVG_DEBUG
+#define TCF_DRY(bit) (P.dry & (bit))
+// event trace of CTA 0 (BVG_TCF_TRACE=1, debug builds): clock64 of pipeline events of blocks / tiles 128..191 at dbg[148 * 16 ...]
+#define TCF_TRACE(ev, idx)                                                                                        \
+  do {                                                                                                            \
+    if (P.trace && blockIdx.x == 0 && (unsigned)((int)(idx) - 128) < 64u && lane == 0)                            \
+      P.trace[(ev) * 64 + (int)(idx) - 128] = clock64();                                                          \
+  } while (0)
+#else
+#define TCF_DRY(bit) false
+#define TCF_TRACE(ev, idx) do { } while (0)
+#endif
 
 struct TcItem { int b, grp, nblk; };
 __device__ __forceinline__ TcItem tc_item(const ActConvTcParams& P, int item) {
@@ -122,6 +139,15 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
                : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return done != 0;
 }
+// try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the hint, ~10 ms,
+// expires) instead of returning after the short default limit -- 20+ warps of this kernel wait on mbarriers most of the time,
+// and polling at the default limit floods the shared-memory pipeline that tcgen05.ld / stmatrix / the arrives go through.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+  return done != 0;
+}
 // Waits of this kernel.  Debug builds (BVG_DEBUG) add a watchdog: a wait that does not complete within ~1 s records
 // (block, warp, wait id) in g_tcf_abort and releases every other wait of the grid, so a protocol bug shows up as a report
 // instead of a hung GPU.
@@ -130,10 +156,12 @@ __device__ int g_tcf_abort[8];
 template <int SLEEP>
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int id) {
   uint32_t spins = 0;
-  while (!mbar_test(bar, parity)) {
-    if (SLEEP) __nanosleep(SLEEP);
-    if ((++spins & 1023u) == 0) {
-      if (spins > (SLEEP ? (1u << 22) : (1u << 26)) || *reinterpret_cast<volatile int*>(&g_tcf_abort[0])) {
+  long long t0 = 0;
+  for (;;) {
+    if (mbar_try_wait_hint(bar, parity)) return;
+    if ((++spins & 3u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 3000000000ll || *reinterpret_cast<volatile int*>(&g_tcf_abort[0])) {
         if (atomicCAS(&g_tcf_abort[0], 0, 1) == 0) {
           g_tcf_abort[1] = blockIdx.x; g_tcf_abort[2] = threadIdx.x >> 5; g_tcf_abort[3] = id; g_tcf_abort[4] = (int)parity;
         }
@@ -146,9 +174,7 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int id) 
 #else
 template <int SLEEP>
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, int) {
-  if (SLEEP == 0) mbar_wait(bar, parity);
-  else if (SLEEP <= 32) mbar_wait_backoff(bar, parity);
-  else mbar_wait_relaxed(bar, parity);
+  while (!mbar_try_wait_hint(bar, parity)) { }
 }
 #define TC_ABORTED() false
 #endif
@@ -158,48 +184,76 @@ struct Ring {
   __device__ __forceinline__ void next(int n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-template <bool HAS_R2>
-__device__ __forceinline__ void epilogue_job(const ActConvTcParams& P, __nv_bfloat16* yb, const __nv_bfloat16* r1,
-                                             const __nv_bfloat16* r2, const float* bias_s, uint32_t tbase, bool valid, int64_t off) {
-  // one accumulator (32 lanes = rows of this warp) in 16-column slices; residual vectors are fetched one slice ahead
+// Conv epilogue of one tile for one warp: the 16-column slices [f0, f1) of the tile's S accumulators (flat index f = segment *
+// (NB / 16) + slice), rows = this warp's 32 TMEM lanes: + bias (+ res1) (+ res2), * scale -> bf16 -> 16-byte stores.  Residual
+// vectors are fetched one slice ahead.  The SM is issue-bound in this kernel, so this is written for instruction count: 32-bit
+// element offsets, packed fp32x2 math, bias as 16-byte shared-memory vectors.
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+template <bool HAS_R1, bool HAS_R2>
+__device__ __forceinline__ void epilogue_slices(const ActConvTcParams& P, const TcItem& it, int n, int r, int f0, int f1,
+                                                __nv_bfloat16* yb, const __nv_bfloat16* r1, const __nv_bfloat16* r2,
+                                                const float* bias_s, uint32_t tbase) {
   const int nsl = P.NB >> 4;
-  const int64_t cs = (int64_t)P.y_tp * 8;                           // elements between channel chunks
-  const float scale = P.scale;
+  const uint32_t cs = (uint32_t)P.y_tp * 8u;                        // elements between channel chunks
+  const f32x2 scale = pk2(P.scale, P.scale);
+  const bool do_scale = P.scale != 1.f;
+  // per-slice element offset of this lane's row (chunk 2 * sl), or ~0 when the row is not an output
+  auto slice_off = [&](int f) -> uint32_t {
+    int sg = 0, sl = f;
+    while (sl >= nsl) { sl -= nsl; ++sg; }                          // (S <= 4: cheaper than a division)
+    const int r0 = seg_r0(P, it, sg);
+    const int q0 = r0 + 128 * n;
+    const bool valid = f < f1 && r0 < P.T && q0 + r < P.T && !TCF_DRY(16);
+    return valid ? (uint32_t)(P.y_pad + q0 + r) * 8u + (uint32_t)(2 * sl) * cs : ~0u;
+  };
+  auto tcol = [&](int f) -> uint32_t {
+    int sg = 0, sl = f;
+    while (sl >= nsl) { sl -= nsl; ++sg; }
+    return (uint32_t)(sg * P.NB + sl * 16);
+  };
   uint4 c1[2], c2[2], n1[2], n2[2];
-  auto load_res = [&](int sl, uint4 (&e1)[2], uint4 (&e2)[2]) {
+  auto load_res = [&](uint32_t off, uint4 (&e1)[2], uint4 (&e2)[2]) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      const int ch = 2 * sl + g;
-      const bool ok = valid && sl < nsl && ch < P.y_chunks;
-      e1[g] = (ok && r1) ? *reinterpret_cast<const uint4*>(r1 + off + ch * cs) : make_uint4(0, 0, 0, 0);
-      if (HAS_R2) e2[g] = ok ? *reinterpret_cast<const uint4*>(r2 + off + ch * cs) : make_uint4(0, 0, 0, 0);
+      if (HAS_R1) e1[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r1 + off + g * cs) : make_uint4(0, 0, 0, 0);
+      if (HAS_R2) e2[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r2 + off + g * cs) : make_uint4(0, 0, 0, 0);
     }
   };
-  load_res(0, c1, c2);
-  for (int sl = 0; sl < nsl; ++sl) {
+  uint32_t coff = slice_off(f0);
+  load_res(coff, c1, c2);
+  for (int f = f0; f < f1; ++f) {
+    const uint32_t col = tcol(f);
     uint32_t v[16];
-    tmem_ld16_nowait(tbase + (uint32_t)(sl * 16), v);
-    load_res(sl + 1, n1, n2);
+    tmem_ld16_nowait(tbase + col, v);
+    const uint32_t noff = slice_off(f + 1);
+    load_res(noff, n1, n2);
+    const float4* bs = reinterpret_cast<const float4*>(bias_s + (col % (uint32_t)P.NB));
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      const int ch = 2 * sl + g;
-      float f[8], e[8];
-      unpack8(c1[g], e);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[8 * g + j]) + bias_s[ch * 8 + j] + e[j];
-      if (HAS_R2) {
-        unpack8(c2[g], e);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += e[j];
+      const float4 b0 = bs[2 * g], b1 = bs[2 * g + 1];
+      f32x2 a0 = add2(pk2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), pk2(b0.x, b0.y));
+      f32x2 a1 = add2(pk2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])), pk2(b0.z, b0.w));
+      f32x2 a2 = add2(pk2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])), pk2(b1.x, b1.y));
+      f32x2 a3 = add2(pk2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])), pk2(b1.z, b1.w));
+      if (HAS_R1) {
+        a0 = add2(a0, bf16x2_to_f32x2(c1[g].x)); a1 = add2(a1, bf16x2_to_f32x2(c1[g].y));
+        a2 = add2(a2, bf16x2_to_f32x2(c1[g].z)); a3 = add2(a3, bf16x2_to_f32x2(c1[g].w));
       }
+      if (HAS_R2) {
+        a0 = add2(a0, bf16x2_to_f32x2(c2[g].x)); a1 = add2(a1, bf16x2_to_f32x2(c2[g].y));
+        a2 = add2(a2, bf16x2_to_f32x2(c2[g].z)); a3 = add2(a3, bf16x2_to_f32x2(c2[g].w));
+      }
+      if (do_scale) { a0 = mul2(a0, scale); a1 = mul2(a1, scale); a2 = mul2(a2, scale); a3 = mul2(a3, scale); }
+      float x0, x1, x2, x3, x4, x5, x6, x7;
+      unpk2(a0, x0, x1); unpk2(a1, x2, x3); unpk2(a2, x4, x5); unpk2(a3, x6, x7);
       uint4 o;
-      o.x = pack2(f[0] * scale, f[1] * scale); o.y = pack2(f[2] * scale, f[3] * scale);
-      o.z = pack2(f[4] * scale, f[5] * scale); o.w = pack2(f[6] * scale, f[7] * scale);
-      if (valid && ch < P.y_chunks) *reinterpret_cast<uint4*>(yb + off + ch * cs) = o;
+      o.x = cvt_bf16x2(x0, x1); o.y = cvt_bf16x2(x2, x3); o.z = cvt_bf16x2(x4, x5); o.w = cvt_bf16x2(x6, x7);
+      if (coff != ~0u) *reinterpret_cast<uint4*>(yb + coff + g * cs) = o;
     }
 #pragma unroll
-    for (int g = 0; g < 2; ++g) { c1[g] = n1[g]; if (HAS_R2) c2[g] = n2[g]; }
+    for (int g = 0; g < 2; ++g) { if (HAS_R1) c1[g] = n1[g]; if (HAS_R2) c2[g] = n2[g]; }
+    coff = noff;
   }
 }
 
@@ -224,12 +278,12 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
   uint64_t* x_ready = x_efull + kMaxXS;          // [4] patch warp done (edge tiles only)
   uint64_t* x_free = x_ready + kMaxXS;           // [4]
   uint64_t* u_full = x_free + kMaxXS;            // [2]
-  uint64_t* u_free = u_full + kNU;               // [2]
-  uint64_t* a_full = u_free + kNU;               // [4]
+  uint64_t* u_free = u_full + kMaxNU;            // [4]
+  uint64_t* a_full = u_free + kMaxNU;            // [4]
   uint64_t* a_free = a_full + 4;                 // [4]
   uint64_t* y_full = a_free + 4;                 // [2]
-  uint64_t* y_free = y_full + kNY;               // [2]
-  uint64_t* as_done = y_free + kNY;              // [3] store warps wrote the whole A stage (no patching needed)
+  uint64_t* y_free = y_full + kMaxNY;            // [4]
+  uint64_t* as_done = y_free + kMaxNY;              // [3] store warps wrote the whole A stage (no patching needed)
   uint64_t* as_edone = as_done + kMaxAS;         // [3] the same for tiles the patch warp completes
   uint64_t* as_ready = as_edone + kMaxAS;        // [3] patch warp done (edge tiles only)
   uint64_t* as_free = as_ready + kMaxAS;         // [3]
@@ -237,17 +291,18 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
   uint64_t* w_free = w_full + kMaxWS;            // [8]
   uint64_t* c_full = w_free + kMaxWS;            // [2]
   uint64_t* c_free = c_full + 2;                 // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c_free + 2);
+  uint64_t* pace = c_free + 2;                   // [2] conv MMA pacing groups
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pace + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);             // [NB]
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_efull[i], 1); mbar_init(&x_ready[i], 1); mbar_init(&x_free[i], 1); }
-    for (int i = 0; i < kNU; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_free[i], 6); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 6); mbar_init(&a_free[i], 1); }
-    for (int i = 0; i < kNY; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_free[i], 6); }
+    for (int i = 0; i < kMaxNU; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_free[i], 12); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 12); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < kMaxNY; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_free[i], 6); }
     for (int i = 0; i < kMaxAS; ++i) { mbar_init(&as_done[i], 6); mbar_init(&as_edone[i], 6); mbar_init(&as_ready[i], 1); mbar_init(&as_free[i], 1); }
     for (int i = 0; i < kMaxWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_free[i], 4 * P.S); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_free[i], 8); mbar_init(&pace[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWPatch) {
@@ -446,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       const uint32_t uph_lo = (smem_u32(up_hi) >> 4) | (64u << 16);
       const uint32_t upl_lo = (smem_u32(up_lo) >> 4) | (64u << 16);
       const uint32_t xs_lo = (smem_u32(xsm) >> 4) | (8u << 16);
-      Ring xr, ur; uint32_t xrdy_ph = 0, xfull_ph = 0;
+      Ring xr, ur; uint32_t xrdy_ph = 0, xfull_ph = 0, tr_nb = 0;
       long long dbg_wx = 0, dbg_wu = 0;
       const long long dbg_start = P.dbg ? clock64() : 0;
       unsigned long long dbg_ns0 = 0;
@@ -464,8 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           }
           { DBG_T0(); tc_wait<0>(&u_free[ur.s], ur.ph ^ 1, 5); DBG_ADD(dbg_wu); }
           tc_fence_after();
+          TCF_TRACE(0, tr_nb); ++tr_nb;
           const uint32_t d = tmem_base + kColU + (uint32_t)ur.s * 64u;
           const uint32_t a0 = xs_lo + (uint32_t)xr.s * (kXStageBytes >> 4) + (uint32_t)pos * 32u;
+          if (!TCF_DRY(2))
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
             umma_ss_elect<kAHi, 0x4008u>(d, a0 + 16u * s, uph_lo + 128u * s, idesc_up, s > 0 ? 1u : 0u);
@@ -473,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           }
           umma_commit_elect(&u_full[ur.s]);
           if (pos == kXB - 1 || nu == nup - 1) { umma_commit_elect(&x_free[xr.s]); xr.next(P.nxs); }
-          ur.next(kNU);
+          ur.next(P.nu);
         }
       }
       if (P.dbg && lane == 0) {
@@ -486,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       const uint32_t idesc_dn = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t dn_lo = (smem_u32(dnm) >> 4) | (32u << 16);
       Ring yr;
-      uint32_t afull_ph = 0;
+      uint32_t afull_ph = 0, tr_j = 0;
       long long dbg_wa = 0, dbg_wy = 0;
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
@@ -500,34 +557,61 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           }
           { DBG_T0(); tc_wait<0>(&y_free[yr.s], yr.ph ^ 1, 7); DBG_ADD(dbg_wy); }
           tc_fence_after();
-          const uint32_t d = tmem_base + kColY + (uint32_t)yr.s * 32u;
-          const uint32_t ap = tmem_base + kColA + (uint32_t)((j - 1) & 3) * 32u + 24u;
-          const uint32_t ac = tmem_base + kColA + (uint32_t)(j & 3) * 32u;
-          const uint32_t an = tmem_base + kColA + (uint32_t)((j + 1) & 3) * 32u;
-          umma_ts_elect<0x4008u>(d, ap, dn_lo, idesc_dn, 0u);
+          TCF_TRACE(4, tr_j); ++tr_j;
+          const uint32_t d = tmem_base + P.colY + (uint32_t)yr.s * 32u;
+          const uint32_t ap = tmem_base + P.colA + (uint32_t)((j - 1) & 3) * 32u + 24u;
+          const uint32_t ac = tmem_base + P.colA + (uint32_t)(j & 3) * 32u;
+          const uint32_t an = tmem_base + P.colA + (uint32_t)((j + 1) & 3) * 32u;
+          if (!TCF_DRY(4)) {
+            umma_ts_elect<0x4008u>(d, ap, dn_lo, idesc_dn, 0u);
 #pragma unroll
-          for (int s = 1; s < 5; ++s) umma_ts_elect<0x4008u>(d, ac + 8u * (s - 1), dn_lo + 64u * s, idesc_dn, 1u);
-          umma_ts_elect<0x4008u>(d, an, dn_lo + 64u * 5, idesc_dn, 1u);
+            for (int s = 1; s < 5; ++s) umma_ts_elect<0x4008u>(d, ac + 8u * (s - 1), dn_lo + 64u * s, idesc_dn, 1u);
+            umma_ts_elect<0x4008u>(d, an, dn_lo + 64u * 5, idesc_dn, 1u);
+          }
           umma_commit_elect(&y_full[yr.s]);
           umma_commit_elect(&a_free[(j - 1) & 3]);
           if (j == it.nblk) {
             umma_commit_elect(&a_free[j & 3]);
             umma_commit_elect(&a_free[(j + 1) & 3]);
           }
-          yr.next(kNY);
+          yr.next(P.ny);
         }
       }
       if (P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[2] = dbg_wa; d[3] = dbg_wy; }
     } else if (warp == kWConv) {
       // ===================== MMA issuer 3: the conv.  D fp32 | A bf16 K-major (A stage) | B bf16 (weights) | N = NB =========
+      // The issue loop is latency-bound on the uniform datapath (an MMA whose operands take ~15 dependent uniform instructions
+      // and a few constant-bank loads to compute costs ~150 cycles where the tensor pipe needs 40-56): everything is hoisted
+      // into locals, the k-steps are unrolled, the taps advance by constant increments.
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_base = (smem_u32(asm_) >> 4) | ((uint32_t)P.SR << 16);
-      const uint32_t w_base = (smem_u32(wsm) >> 4) | ((uint32_t)P.NB << 16);
+      const uint32_t SR = (uint32_t)P.SR, NB = (uint32_t)P.NB;
+      const uint32_t a_base = ((smem_u32(asm_) >> 4) | (SR << 16)) + (uint32_t)(P.LH - P.lo);
+      const uint32_t w_base = (smem_u32(wsm) >> 4) | (NB << 16);
       const uint32_t as16 = P.a_stage_bytes >> 4, ws16 = P.w_slot_bytes >> 4;
-      const int ncb = (P.Cin_p + 63) >> 6;
+      const uint32_t SR2 = 2u * SR, NB2 = 2u * NB, dil = (uint32_t)P.dil, seg_a = (uint32_t)P.rc * SR, c_base = tmem_base + P.colC;
+      const int K = P.K, S = P.S, nas = P.nas, nacc = P.nacc, w_slots = P.w_slots;
+      const int nk0 = min(8, P.Cin_p >> 3) >> 1, nk1 = ((P.Cin_p >> 3) - 2 * nk0) >> 1;        // 16-channel steps of the two 64-channel blocks
+      const bool resident = P.w_resident != 0;
       Ring ar, cr, wr; uint32_t ardy_ph = 0, adone_ph = 0;
       bool w_waited = false;
+      uint32_t tr_t = 0;
       long long dbg_ws = 0, dbg_wc = 0, dbg_ww = 0;
+      // the K taps of one 64-channel block for one accumulator: nk MMAs per tap, A advances `dil` rows per tap
+      auto taps = [&](int nk, uint32_t d, uint32_t a_t, uint32_t b, uint32_t& acc) {
+        for (int tp = 0; tp < K; ++tp) {
+          if (!resident) { tc_wait<0>(&w_full[wr.s], wr.ph, 12); tc_fence_after(); b = w_base + (uint32_t)wr.s * ws16; }
+          if (!TCF_DRY(1)) {
+            umma_bf16_imm_elect(d, a_t, b, idesc, acc);
+            umma_bf16_imm_elect(d, a_t + SR2, b + NB2, idesc, 1u);
+            if (nk > 2) umma_bf16_imm_elect(d, a_t + 2u * SR2, b + 2u * NB2, idesc, 1u);
+            if (nk > 3) umma_bf16_imm_elect(d, a_t + 3u * SR2, b + 3u * NB2, idesc, 1u);
+          }
+          acc = 1u;
+          a_t += dil;
+          if (resident) b += (uint32_t)nk * NB2;
+          else { umma_commit_elect(&w_free[wr.s]); wr.next(w_slots); }
+        }
+      };
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
         for (int n = 0; n < (it.nblk >> 2); ++n) {
@@ -538,46 +622,30 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             DBG_ADD(dbg_ws);
           }
           { DBG_T0(); tc_wait<20>(&c_free[cr.s], cr.ph ^ 1, 10); DBG_ADD(dbg_wc); }
-          if (P.w_resident && !w_waited) { DBG_T0(); tc_wait<0>(&w_full[0], 0u, 11); w_waited = true; DBG_ADD(dbg_ww); }
+          if (resident && !w_waited) { DBG_T0(); tc_wait<0>(&w_full[0], 0u, 11); w_waited = true; DBG_ADD(dbg_ww); }
           tc_fence_after();
-          for (int s = 0; s < P.S; ++s) {
-            const uint32_t d = tmem_base + kColC + (uint32_t)(cr.s * P.S * P.NB + s * P.NB);
-            const uint32_t a_seg = a_base + (uint32_t)ar.s * as16 + (uint32_t)(s * P.rc * P.SR + P.LH - P.lo);
+          TCF_TRACE(7, tr_t + 96);
+          uint32_t d = c_base + (uint32_t)cr.s * (uint32_t)S * NB;
+          uint32_t a_s = a_base + (uint32_t)ar.s * as16;
+          for (int sg = 0; sg < S; ++sg, d += NB, a_s += seg_a) {
             uint32_t acc = 0u;
-            for (int cb = 0; cb < ncb; ++cb) {
-              const int kcn = min(8, (P.Cin_p >> 3) - cb * 8);
-              for (int tp = 0; tp < P.K; ++tp) {
-                uint32_t b_lo;
-                if (P.w_resident) {
-                  b_lo = w_base + (uint32_t)(cb * 8 * P.NB * P.K + tp * kcn * P.NB);
-                } else {
-                  DBG_T0();
-                  tc_wait<0>(&w_full[wr.s], wr.ph, 12);
-                  DBG_ADD(dbg_ww);
-                  tc_fence_after();
-                  b_lo = w_base + (uint32_t)wr.s * ws16;
-                }
-                const uint32_t a_t = a_seg + (uint32_t)(cb * 8 * P.SR + tp * P.dil);
-                for (int ks = 0; ks < (kcn >> 1); ++ks) {
-                  umma_bf16_imm_elect(d, a_t + (uint32_t)(ks * 2 * P.SR), b_lo + (uint32_t)(ks * 2 * P.NB), idesc, acc);
-                  acc = 1u;
-                }
-                if (!P.w_resident) { umma_commit_elect(&w_free[wr.s]); wr.next(P.w_slots); }
-              }
-            }
+            taps(nk0, d, a_s, w_base, acc);
+            if (nk1 > 0) taps(nk1, d, a_s + 8u * SR, w_base + (uint32_t)(8 * K) * NB, acc);
           }
           umma_commit_elect(&c_full[cr.s]);
           umma_commit_elect(&as_free[ar.s]);
-          ar.next(P.nas);
-          cr.next(P.nacc);
+          TCF_TRACE(8, tr_t + 96); ++tr_t;
+          ar.next(nas);
+          cr.next(nacc);
         }
       }
       if (P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[9] = dbg_ws; d[10] = dbg_wc; d[11] = dbg_ww; }
     }
   } else if (warp < kWStore0) {
     // ===================== snake: U (fp32, TMEM) -> a = u + hb - hb cos(2 e^alpha u) -> fp16 pairs (TMEM ring) ==============
-    // 12 warps: TMEM lane quarter q = warp % 4 (0..2), two groups taking alternate blocks, 32-column half h per warp
-    const int q = warp & 3, grp = (warp >> 2) & 1, h = warp >> 3;
+    // 12 warps on every block: TMEM lane quarter q = warp % 4 (0..2), 16-column quarter cq = warp / 4 of the block's 64 upsampled
+    // samples (a short per-block latency matters more than staggered MUFU phases: the rings are TMEM-bound and shallow)
+    const int q = warp & 3, cq = warp >> 2;
     const int ln = q * 32 + lane;
     const int slot = ln >> 3;
     const int cc = slot % P.rc;
@@ -590,6 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     const f32x2 SC0 = pk2(sc0, sc0), SC1 = pk2(sc1, sc1), NSC1 = pk2(-sc1, -sc1);
     uint32_t nb = 0;
     uint32_t afree_ph = 0;
+    Ring ur;
     long long dbg_su = 0, dbg_sa = 0;
     const long long dbg_sstart = P.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
@@ -598,43 +667,38 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         const int sl = i & 3;
         const uint32_t aph = (afree_ph >> sl) & 1u;
         afree_ph ^= 1u << sl;
-        if ((int)(nb & 1u) != grp) continue;
-        const uint32_t ub = nb & 1u, uph = (nb >> 1) & 1u;
-        { DBG_T0(); tc_wait<0>(&u_full[ub], uph, 13); DBG_ADD(dbg_su); }
+        if (warp == 0) {                                               // one polling warp per role group (see the epilogue)
+          { DBG_T0(); tc_wait<0>(&u_full[ur.s], ur.ph, 13); DBG_ADD(dbg_su); }
+          { DBG_T0(); tc_wait<0>(&a_free[sl], aph ^ 1u, 14); DBG_ADD(dbg_sa); }
+        }
+        named_bar_sync(1, 384);
+        if (warp == 0) TCF_TRACE(1, nb);
         tc_fence_after();
-        // two 16-column half steps (the warp runs at 64 registers: no setmaxnreg -- roles do not align to warpgroups)
-        const uint32_t ucol = tq + kColU + ub * 64u + (uint32_t)h * 32u;
-        const uint32_t acol = tq + kColA + (uint32_t)sl * 32u + (uint32_t)h * 16u;
-        uint32_t v0[16], v1[16];
-        tmem_ld16_nowait(ucol, v0);
-        { DBG_T0(); tc_wait<0>(&a_free[sl], aph ^ 1u, 14); DBG_ADD(dbg_sa); }
-        tc_fence_after();
-        tmem_ld_wait();
-        tmem_ld16_nowait(ucol + 16u, v1);
-        auto half_step = [&](const uint32_t (&v)[16], uint32_t dst) {
-          uint32_t w[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const f32x2 u = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-            float zx, zy;
-            unpk2(mul2(u, SC0), zx, zy);
-            const f32x2 a = fma2(NSC1, pk2(__cosf(zx), __cosf(zy)), add2(u, SC1));
-            float ax, ay;
-            unpk2(a, ax, ay);
-            w[k] = cvt_f16x2_sat(ax, ay);
-          }
-          tmem_st8(dst, w);
-        };
-        half_step(v0, acol);
+        uint32_t v[16];
+        tmem_ld16_nowait(tq + kColU + (uint32_t)ur.s * 64u + (uint32_t)cq * 16u, v);
         tmem_ld_wait();                                                // U is in registers: the buffer can be rewritten
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&u_free[ub]);
-        half_step(v1, acol + 8u);
+        if (lane == 0) mbar_arrive(&u_free[ur.s]);
+        ur.next(P.nu);
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const f32x2 u = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+          float zx, zy;
+          unpk2(mul2(u, SC0), zx, zy);
+          const f32x2 a = TCF_DRY(8) ? fma2(NSC1, pk2(zx, zy), add2(u, SC1)) : fma2(NSC1, pk2(__cosf(zx), __cosf(zy)), add2(u, SC1));
+          float ax, ay;
+          unpk2(a, ax, ay);
+          w[k] = cvt_f16x2_sat(ax, ay);
+        }
+        if (warp == 0) TCF_TRACE(2, nb);
+        tmem_st8(tq + P.colA + (uint32_t)sl * 32u + (uint32_t)cq * 8u, w);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[sl]);
+        if (warp == 0) TCF_TRACE(3, nb);
       }
     }
     if (P.dbg && threadIdx.x == 0) { long long* d = P.dbg + blockIdx.x * 16; d[5] = dbg_su; d[6] = dbg_sa; d[15] = clock64() - dbg_sstart; }
@@ -643,17 +707,18 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     // 6 warps: TMEM lane quarter q = warp % 4 (0..2), 16-step half h of every block.  tcgen05.ld.16x256b returns the mma
     // C-fragment layout, which is what stmatrix.trans needs to write 8 channels x 8 time steps as eight 16-byte rows.
     const int q = warp & 3, h = (warp >> 2) & 1;
-    const uint32_t tqa = tmem_base + ((uint32_t)(q * 32) << 16) + kColY + (uint32_t)h * 16u;
+    const uint32_t tqa = tmem_base + ((uint32_t)(q * 32) << 16) + P.colY + (uint32_t)h * 16u;
     const uint32_t tqb = tqa + (16u << 16);
     const int slotA = 4 * q + ((lane >> 3) & 1);                       // this lane's stmatrix row: chunk-slot (+2 for the second store)
     const int rowin = 16 * h + (lane >> 4) * 8 + (lane & 7);           // ... and row within the block
     uint8_t* const mydump = dump + lane * 16;
     const int LH = P.LH, SR = P.SR;
     Ring yr, open, mainr, closer;
+    uint32_t tr_j = 0;
     long long dbg_ty = 0, dbg_tf = 0;
     auto put = [&](uint8_t* stage, int row0, int vlo, int vhi, const uint32_t (&pa)[4], const uint32_t (&pb)[4]) {
       // rows [vlo, vhi) of the block go to stage rows row0 + rowin; the other matrices of the store go to the dump
-      if (16 * h >= vhi || 16 * h + 16 <= vlo) return;
+      if (16 * h >= vhi || 16 * h + 16 <= vlo || TCF_DRY(32)) return;
       const bool ok = rowin >= vlo && rowin < vhi;
       uint8_t* a = ok ? stage + ((size_t)slotA * SR + row0 + rowin) * 16 : mydump;
       uint8_t* b = ok ? a + (size_t)2 * SR * 16 : mydump;
@@ -663,19 +728,23 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
       for (int j = -1; j <= it.nblk; ++j) {
-        { DBG_T0(); tc_wait<0>(&y_full[yr.s], yr.ph, 15); DBG_ADD(dbg_ty); }
+        const int p = j & 3;
+        const bool opens = p == 3 && j + 1 < it.nblk;                  // first rows of tile (j + 1) / 4's stage
+        if (warp == kWStore0) {                                        // one polling warp per role group
+          { DBG_T0(); tc_wait<0>(&y_full[yr.s], yr.ph, 15); DBG_ADD(dbg_ty); }
+          if (opens) { DBG_T0(); tc_wait<0>(&as_free[open.s], open.ph ^ 1, 16); DBG_ADD(dbg_tf); }
+        }
+        named_bar_sync(2, 192);
+        if (warp == kWStore0) TCF_TRACE(5, tr_j);
         tc_fence_after();
         uint32_t va[8], vb[8];
         tmem_ld_16x256b_x2_nowait(tqa + (uint32_t)yr.s * 32u, va);
         tmem_ld_16x256b_x2_nowait(tqb + (uint32_t)yr.s * 32u, vb);
-        const int p = j & 3;
-        const bool opens = p == 3 && j + 1 < it.nblk;                  // first rows of tile (j + 1) / 4's stage
-        if (opens) { DBG_T0(); tc_wait<0>(&as_free[open.s], open.ph ^ 1, 16); DBG_ADD(dbg_tf); }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&y_free[yr.s]);
-        yr.next(kNY);
+        yr.next(P.ny);
         uint32_t pa[4], pb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -696,58 +765,59 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           closer.next(P.nas);
         }
         if (p == 3 && j >= 0) mainr.next(P.nas);
+        if (warp == kWStore0) TCF_TRACE(6, tr_j);
+        ++tr_j;
       }
     }
     if (P.dbg && threadIdx.x == kWStore0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[7] = dbg_ty; d[8] = dbg_tf; }
   } else {
-    // ===================== conv epilogue: 8 warps = 2 sets x 4 TMEM lane quarters; jobs (tile, segment) alternate sets =======
+    // ===================== conv epilogue: 8 warps = 2 sets x 4 TMEM lane quarters; every tile is split between the sets =======
+    // (the tile's S x NB / 16 column slices are dealt out half and half, so the single accumulator stage drains twice as fast)
     const int set = (warp - kWEpi0) >> 2, q = warp & 3;
     const int r = q * 32 + lane;                                       // accumulator row
-    const int64_t cs = (int64_t)P.y_tp * 8;
+    const int nslt = P.S * (P.NB >> 4);
+    const int f0 = set ? nslt >> 1 : 0, f1 = set ? nslt : nslt >> 1;
     Ring cr;
-    uint32_t job = 0;
+    uint32_t tile = 0;
     long long dbg_ew = 0, dbg_eb = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
       __nv_bfloat16* yb = P.y + (int64_t)it.b * P.y_bstride;
       const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)it.b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)it.b * P.y_bstride : nullptr;
-      for (int n = 0; n < (it.nblk >> 2); ++n) {
-        for (int s = 0; s < P.S; ++s, ++job) {
-          if ((int)(job & 1u) != set) continue;
-          const int r0 = seg_r0(P, it, s);
-          const int q0 = r0 + 128 * n;
-          const bool valid = r0 < P.T && q0 + r < P.T;
-          const int64_t off = (int64_t)(P.y_pad + q0 + r) * 8;
-          if (valid && (r1 || r2)) {
-            // pull this job's residual rows towards L2 before waiting for the MMAs
-            for (int ch = 0; ch < P.y_chunks; ++ch) {
-              if (r1) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + off + ch * cs));
-              if (r2) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + off + ch * cs));
-            }
-          }
-          { DBG_T0(); tc_wait<64>(&c_full[cr.s], cr.ph, 17); DBG_ADD(dbg_ew); }
-          tc_fence_after();
-          DBG_T0();
-          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + kColC + (uint32_t)(cr.s * P.S * P.NB + s * P.NB);
-          if (r2) epilogue_job<true>(P, yb, r1, r2, bias_s, tbase, valid, off);
-          else epilogue_job<false>(P, yb, r1, nullptr, bias_s, tbase, valid, off);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&c_free[cr.s]);
-          if (P.zero_pads && r0 < P.T) {
-            // rows [-pad, 0) by the first tile of the utterance, [T, T + pad) by the tile that holds row T - 1
-            const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int n = 0; n < (it.nblk >> 2); ++n, ++tile) {
+        // one warp polls the mbarrier, the other seven park on a named barrier (no issue slots: the SM is issue-bound)
+        if (warp == kWEpi0) { DBG_T0(); tc_wait<64>(&c_full[cr.s], cr.ph, 17); DBG_ADD(dbg_ew); }
+        named_bar_sync(3, 256);
+        if (q == 0 && set == 0) TCF_TRACE(9, tile + 96);
+        tc_fence_after();
+        DBG_T0();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + P.colC + (uint32_t)(cr.s * P.S * P.NB);
+        if (r2) epilogue_slices<true, true>(P, it, n, r, f0, f1, yb, r1, r2, bias_s, tbase);
+        else if (r1) epilogue_slices<true, false>(P, it, n, r, f0, f1, yb, r1, nullptr, bias_s, tbase);
+        else epilogue_slices<false, false>(P, it, n, r, f0, f1, yb, nullptr, nullptr, bias_s, tbase);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_free[cr.s]);
+        if (q == 0 && set == 0) TCF_TRACE(10, tile + 96);
+        cr.next(P.nacc);
+        if (P.zero_pads) {
+          // rows [-pad, 0) by the first tile of the utterance, [T, T + pad) by the tile that holds row T - 1 (256 threads)
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          const int et = set * 128 + r;
+          for (int sg = 0; sg < P.S; ++sg) {
+            const int r0 = seg_r0(P, it, sg);
+            if (r0 >= P.T) break;
+            const int q0 = r0 + 128 * n;
             if (q0 == 0)
-              for (int i = r; i < P.y_chunks * P.y_pad; i += 128)
+              for (int i = et; i < P.y_chunks * P.y_pad; i += 256)
                 *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + (i % P.y_pad)) * 8) = z;
             if (q0 < P.T && q0 + 128 >= P.T)
-              for (int i = r; i < P.y_chunks * P.y_pad; i += 128)
+              for (int i = et; i < P.y_chunks * P.y_pad; i += 256)
                 *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + P.y_pad + P.T + (i % P.y_pad)) * 8) = z;
           }
-          DBG_ADD(dbg_eb);
         }
-        cr.next(P.nacc);
+        DBG_ADD(dbg_eb);
       }
     }
     if (P.dbg && threadIdx.x == kWEpi0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[12] = dbg_ew; d[14] = dbg_eb; }
@@ -809,8 +879,19 @@ int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, 
   if (n_nblk != 1) return BVG_ERR_STATE;
   P.C = L.Cin; P.rc = L.Cin / 8; P.S = kSlots / P.rc;
   P.Cin_p = (L.Cin + 15) / 16 * 16;
-  if (P.S * P.NB > 192 || y.chunks * 8 < P.NB || x.chunks * 8 < P.Cin_p) return BVG_ERR_STATE;
-  P.nacc = 2 * P.S * P.NB <= 192 ? 2 : 1;
+  if (P.S * P.NB > 128 || y.chunks * 8 < P.NB || x.chunks * 8 < P.Cin_p) return BVG_ERR_STATE;
+  // TMEM plan (512 columns): one conv accumulator stage; what is left goes to the FIR rings (their depth sets how much of the
+  // MMA -> barrier -> warp -> MMA round trips overlaps): U 3 x 64 | A 4 x 32 | Y 3 x 32 | conv 96, or U 2 x 64 | A | Y 4 x 32 | conv 128
+  // Measured (profiles/README.md, round 2): two conv accumulator stages beat deeper FIR rings (the epilogue of tile n then
+  // overlaps the MMAs of tile n + 1), so C = 96 / 48 run U 2 x 64 | A 4 x 32 | Y 2 x 32 | conv 2 x 96.
+  if (P.S * P.NB <= 96 && BVG_ENV_ONCE("BVG_TCF_NACC", 2) == 2) { P.nacc = 2; P.nu = 2; P.ny = 2; }
+  else if (P.S * P.NB <= 96) { P.nacc = 1; P.nu = 3; P.ny = 3; }
+  else { P.nacc = 1; P.nu = 2; P.ny = 4; }
+  if (const int e = BVG_ENV_ONCE("BVG_TCF_NU", 0)) P.nu = std::min(kMaxNU, std::max(2, e));     // (experiments)
+  if (const int e = BVG_ENV_ONCE("BVG_TCF_NY", 0)) P.ny = std::min(kMaxNY, std::max(2, e));
+  P.colA = (uint32_t)P.nu * 64u; P.colY = P.colA + 128u; P.colC = P.colY + (uint32_t)P.ny * 32u;
+  if (P.colC + (uint32_t)(P.nacc * P.S * P.NB) > 512u) return BVG_ERR_STATE;
+  P.pace = 0;
   P.Cout = L.Cout; P.K = L.K; P.dil = L.dil;
   P.lo = L.dil * (L.K - 1) / 2;
   if ((L.dil * (L.K - 1)) & 1 || P.lo > 32) return BVG_ERR_STATE;
@@ -825,8 +906,12 @@ int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, 
   P.edge = static_cast<const __nv_bfloat16*>(scratch);
   P.T = x.T; P.zero_pads = ep.zero_pads;
   P.dbg = g_dbg_buf;
+#ifdef BVG_DEBUG
+  if (const char* e = getenv("BVG_TCF_DRY")) P.dry = atoi(e);
+  if (getenv("BVG_TCF_TRACE") && g_dbg_buf) P.trace = g_dbg_buf + 148 * 16;      // (read per launch: the sweep tool changes it between launches)
+#endif
   // shared memory plan: taps + barriers fixed; A stages 3 deep, input ring 4 (min 2) deep, weights resident when they fit
-  const size_t fixed = 2 * kUpBytes + kDnBytes + kDumpBytes + 64 * 8 + 16 + (size_t)P.NB * 4 + 128;
+  const size_t fixed = 2 * kUpBytes + kDnBytes + kDumpBytes + 80 * 8 + 16 + (size_t)P.NB * 4 + 128;
   const size_t budget = 227 * 1024 - fixed;
   P.w_total_bytes = (uint32_t)((size_t)P.Cin_p * P.NB * P.K * 2);
   P.w_slot_bytes = (uint32_t)std::min(8, P.Cin_p / 8) * P.NB * 16u;
