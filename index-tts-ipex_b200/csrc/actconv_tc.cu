@@ -184,50 +184,50 @@ struct Ring {
   __device__ __forceinline__ void next(int n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-// Conv epilogue of one tile for one warp: the 16-column slices [f0, f1) of the tile's S accumulators (flat index f = segment *
-// (NB / 16) + slice), rows = this warp's 32 TMEM lanes: + bias (+ res1) (+ res2), * scale -> bf16 -> 16-byte stores.  Residual
-// vectors are fetched one slice ahead.  The SM is issue-bound in this kernel, so this is written for instruction count: 32-bit
-// element offsets, packed fp32x2 math, bias as 16-byte shared-memory vectors.
+// Conv epilogue of one tile for one warp: `cnt` consecutive 16-column slices of the tile's S accumulators starting at segment
+// sg0, slice sl0 (flat slice f <-> TMEM columns 16 f .. 16 f + 15), rows = this warp's 32 TMEM lanes: + bias (+ res1) (+ res2),
+// * scale -> bf16 -> 16-byte stores.  Residual vectors are fetched one slice ahead.  The SM is issue-bound and the uniform
+// datapath slow (address arithmetic on warp-uniform values costs ~10 cycles per dependent instruction), so everything that
+// can be hoisted is passed in: per-tile state is three integers, per-slice state advances by constant increments.
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+struct EpiConst {
+  int sg0, sl0, cnt, nsl;            // this warp's slices
+  int T, RL, row_base;               // row_base = y_pad (element row of t = 0)
+  uint32_t cs2;                      // elements between channel-chunk PAIRS (2 * y_tp * 8)
+  uint32_t cs;
+  float scale; bool do_scale;
+};
 template <bool HAS_R1, bool HAS_R2>
-__device__ __forceinline__ void epilogue_slices(const ActConvTcParams& P, const TcItem& it, int n, int r, int f0, int f1,
-                                                __nv_bfloat16* yb, const __nv_bfloat16* r1, const __nv_bfloat16* r2,
-                                                const float* bias_s, uint32_t tbase) {
-  const int nsl = P.NB >> 4;
-  const uint32_t cs = (uint32_t)P.y_tp * 8u;                        // elements between channel chunks
-  const f32x2 scale = pk2(P.scale, P.scale);
-  const bool do_scale = P.scale != 1.f;
-  // per-slice element offset of this lane's row (chunk 2 * sl), or ~0 when the row is not an output
-  auto slice_off = [&](int f) -> uint32_t {
-    int sg = 0, sl = f;
-    while (sl >= nsl) { sl -= nsl; ++sg; }                          // (S <= 4: cheaper than a division)
-    const int r0 = seg_r0(P, it, sg);
-    const int q0 = r0 + 128 * n;
-    const bool valid = f < f1 && r0 < P.T && q0 + r < P.T && !TCF_DRY(16);
-    return valid ? (uint32_t)(P.y_pad + q0 + r) * 8u + (uint32_t)(2 * sl) * cs : ~0u;
-  };
-  auto tcol = [&](int f) -> uint32_t {
-    int sg = 0, sl = f;
-    while (sl >= nsl) { sl -= nsl; ++sg; }
-    return (uint32_t)(sg * P.NB + sl * 16);
+__device__ __forceinline__ void epilogue_tile(const EpiConst& E, int seg_t0, int t_in_seg, __nv_bfloat16* yb, const __nv_bfloat16* r1,
+                                              const __nv_bfloat16* r2, const float* bias_s, uint32_t tbase) {
+  // seg_t0: first row of segment sg0 of the item; t_in_seg: this lane's row within the segment (128 n + r)
+  const f32x2 scale = pk2(E.scale, E.scale);
+  int sl = E.sl0, r0 = seg_t0;
+  uint32_t tcol = tbase + (uint32_t)((E.sg0 * E.nsl + E.sl0) * 16);
+  const float* bp = bias_s + E.sl0 * 16;
+  auto offset = [&](int r0_, int sl_) -> uint32_t {                 // element offset of (row, chunk 2 sl), ~0 if not an output row
+    const int t = r0_ + t_in_seg;
+    return (r0_ < E.T && t < E.T && !TCF_DRY(16)) ? (uint32_t)(E.row_base + t) * 8u + (uint32_t)sl_ * E.cs2 : ~0u;
   };
   uint4 c1[2], c2[2], n1[2], n2[2];
   auto load_res = [&](uint32_t off, uint4 (&e1)[2], uint4 (&e2)[2]) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      if (HAS_R1) e1[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r1 + off + g * cs) : make_uint4(0, 0, 0, 0);
-      if (HAS_R2) e2[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r2 + off + g * cs) : make_uint4(0, 0, 0, 0);
+      if (HAS_R1) e1[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r1 + off + g * E.cs) : make_uint4(0, 0, 0, 0);
+      if (HAS_R2) e2[g] = off != ~0u ? *reinterpret_cast<const uint4*>(r2 + off + g * E.cs) : make_uint4(0, 0, 0, 0);
     }
   };
-  uint32_t coff = slice_off(f0);
+  uint32_t coff = offset(r0, sl);
   load_res(coff, c1, c2);
-  for (int f = f0; f < f1; ++f) {
-    const uint32_t col = tcol(f);
+  for (int i = 0; i < E.cnt; ++i) {
     uint32_t v[16];
-    tmem_ld16_nowait(tbase + col, v);
-    const uint32_t noff = slice_off(f + 1);
+    tmem_ld16_nowait(tcol, v);
+    const float4* bs = reinterpret_cast<const float4*>(bp);
+    // next slice
+    tcol += 16u; bp += 16;
+    if (++sl == E.nsl) { sl = 0; r0 += E.RL; bp = bias_s; }
+    const uint32_t noff = i + 1 < E.cnt ? offset(r0, sl) : ~0u;
     load_res(noff, n1, n2);
-    const float4* bs = reinterpret_cast<const float4*>(bias_s + (col % (uint32_t)P.NB));
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -244,12 +244,12 @@ __device__ __forceinline__ void epilogue_slices(const ActConvTcParams& P, const 
         a0 = add2(a0, bf16x2_to_f32x2(c2[g].x)); a1 = add2(a1, bf16x2_to_f32x2(c2[g].y));
         a2 = add2(a2, bf16x2_to_f32x2(c2[g].z)); a3 = add2(a3, bf16x2_to_f32x2(c2[g].w));
       }
-      if (do_scale) { a0 = mul2(a0, scale); a1 = mul2(a1, scale); a2 = mul2(a2, scale); a3 = mul2(a3, scale); }
+      if (E.do_scale) { a0 = mul2(a0, scale); a1 = mul2(a1, scale); a2 = mul2(a2, scale); a3 = mul2(a3, scale); }
       float x0, x1, x2, x3, x4, x5, x6, x7;
       unpk2(a0, x0, x1); unpk2(a1, x2, x3); unpk2(a2, x4, x5); unpk2(a3, x6, x7);
       uint4 o;
       o.x = cvt_bf16x2(x0, x1); o.y = cvt_bf16x2(x2, x3); o.z = cvt_bf16x2(x4, x5); o.w = cvt_bf16x2(x6, x7);
-      if (coff != ~0u) *reinterpret_cast<uint4*>(yb + coff + g * cs) = o;
+      if (coff != ~0u) *reinterpret_cast<uint4*>(yb + coff + g * E.cs) = o;
     }
 #pragma unroll
     for (int g = 0; g < 2; ++g) { if (HAS_R1) c1[g] = n1[g]; if (HAS_R2) c2[g] = n2[g]; }
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_efull[i], 1); mbar_init(&x_ready[i], 1); mbar_init(&x_free[i], 1); }
-    for (int i = 0; i < kMaxNU; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_free[i], 12); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 12); mbar_init(&a_free[i], 1); }
+    for (int i = 0; i < kMaxNU; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_free[i], 6); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 6); mbar_init(&a_free[i], 1); }
     for (int i = 0; i < kMaxNY; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_free[i], 6); }
     for (int i = 0; i < kMaxAS; ++i) { mbar_init(&as_done[i], 6); mbar_init(&as_edone[i], 6); mbar_init(&as_ready[i], 1); mbar_init(&as_free[i], 1); }
     for (int i = 0; i < kMaxWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1); }
@@ -376,9 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             const int r0 = seg_r0(P, it, ps);
             const int ts = xstage_t0(r0, st);
             const int lo = max(ts, 0), hi = min(ts + kXR, P.T);
-            if (r0 < P.T && hi > lo)
+            if (r0 < P.T && hi > lo) {
               bulk_g2s(smem_u32(xsm + xr.s * kXStageBytes) + (uint32_t)((lane * kXR + (lo - ts)) * 16),
                        xb + ((int64_t)pcc * P.x_tp + P.x_pad + lo) * 8, (uint32_t)(hi - lo) * 16u, full);
+            }
           }
           xr.next(P.nxs);
         }
@@ -643,13 +644,18 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     }
   } else if (warp < kWStore0) {
     // ===================== snake: U (fp32, TMEM) -> a = u + hb - hb cos(2 e^alpha u) -> fp16 pairs (TMEM ring) ==============
-    // 12 warps on every block: TMEM lane quarter q = warp % 4 (0..2), 16-column quarter cq = warp / 4 of the block's 64 upsampled
-    // samples (a short per-block latency matters more than staggered MUFU phases: the rings are TMEM-bound and shallow)
-    const int q = warp & 3, cq = warp >> 2;
+    // 12 warps: TMEM lane quarter q = warp % 4 (0..2); two groups of 6 take alternate blocks (while one group sits in its
+    // tcgen05.ld / tcgen05.st round trips the other keeps the MUFU pipe busy), 32-column half h per warp, done as two
+    // 16-column half steps (the warp runs at 64 registers).  One warp per group polls the mbarriers, the rest park on a
+    // named barrier.
+    const int q = warp & 3, grp = (warp >> 2) & 1, h = warp >> 3;
+    const bool leader = q == 0 && h == 0;
     const int ln = q * 32 + lane;
     const int slot = ln >> 3;
     const int cc = slot % P.rc;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t colA = P.colA;
+    const int nu = P.nu;
     float sc0 = 0.f, sc1 = 0.f;
     {
       const int ch = cc * 8 + (ln & 7);
@@ -661,39 +667,47 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     Ring ur;
     long long dbg_su = 0, dbg_sa = 0;
     const long long dbg_sstart = P.dbg ? clock64() : 0;
+    auto half_step = [&](const uint32_t (&v)[16], uint32_t dst) {
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const f32x2 u = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+        float zx, zy;
+        unpk2(mul2(u, SC0), zx, zy);
+        const f32x2 a = TCF_DRY(8) ? fma2(NSC1, pk2(zx, zy), add2(u, SC1)) : fma2(NSC1, pk2(__cosf(zx), __cosf(zy)), add2(u, SC1));
+        float ax, ay;
+        unpk2(a, ax, ay);
+        w[k] = cvt_f16x2_sat(ax, ay);
+      }
+      tmem_st8(dst, w);
+    };
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
-      for (int i = -2; i <= it.nblk + 1; ++i, ++nb) {
+      const int iend = it.nblk + 1;
+      for (int i = -2; i <= iend; ++i, ++nb, ur.next(nu)) {
         const int sl = i & 3;
         const uint32_t aph = (afree_ph >> sl) & 1u;
         afree_ph ^= 1u << sl;
-        if (warp == 0) {                                               // one polling warp per role group (see the epilogue)
+        if ((int)(nb & 1u) != grp) continue;
+        if (leader) {
           { DBG_T0(); tc_wait<0>(&u_full[ur.s], ur.ph, 13); DBG_ADD(dbg_su); }
           { DBG_T0(); tc_wait<0>(&a_free[sl], aph ^ 1u, 14); DBG_ADD(dbg_sa); }
         }
-        named_bar_sync(1, 384);
+        if (grp) named_bar_sync(4, 192); else named_bar_sync(1, 192);
         if (warp == 0) TCF_TRACE(1, nb);
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16_nowait(tq + kColU + (uint32_t)ur.s * 64u + (uint32_t)cq * 16u, v);
+        const uint32_t ucol = tq + kColU + (uint32_t)ur.s * 64u + (uint32_t)h * 32u;
+        const uint32_t acol = tq + colA + (uint32_t)sl * 32u + (uint32_t)h * 16u;
+        uint32_t v0[16], v1[16];
+        tmem_ld16_nowait(ucol, v0);
+        tmem_ld16_nowait(ucol + 16u, v1);
         tmem_ld_wait();                                                // U is in registers: the buffer can be rewritten
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&u_free[ur.s]);
-        ur.next(P.nu);
-        uint32_t w[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const f32x2 u = pk2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-          float zx, zy;
-          unpk2(mul2(u, SC0), zx, zy);
-          const f32x2 a = TCF_DRY(8) ? fma2(NSC1, pk2(zx, zy), add2(u, SC1)) : fma2(NSC1, pk2(__cosf(zx), __cosf(zy)), add2(u, SC1));
-          float ax, ay;
-          unpk2(a, ax, ay);
-          w[k] = cvt_f16x2_sat(ax, ay);
-        }
+        half_step(v0, acol);
+        half_step(v1, acol + 8u);
         if (warp == 0) TCF_TRACE(2, nb);
-        tmem_st8(tq + P.colA + (uint32_t)sl * 32u + (uint32_t)cq * 8u, w);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -775,49 +789,82 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     // (the tile's S x NB / 16 column slices are dealt out half and half, so the single accumulator stage drains twice as fast)
     const int set = (warp - kWEpi0) >> 2, q = warp & 3;
     const int r = q * 32 + lane;                                       // accumulator row
-    const int nslt = P.S * (P.NB >> 4);
-    const int f0 = set ? nslt >> 1 : 0, f1 = set ? nslt : nslt >> 1;
+    EpiConst E;
+    {
+      const int nslt = P.S * (P.NB >> 4);
+      // every tile is split between the two sets (half the column slices each): the accumulator stage drains twice as fast
+      const int f0 = set ? nslt >> 1 : 0, f1 = set ? nslt : nslt >> 1;
+      E.nsl = P.NB >> 4;
+      E.sg0 = f0 / E.nsl; E.sl0 = f0 - E.sg0 * E.nsl; E.cnt = f1 - f0;
+      E.T = P.T; E.RL = P.RL; E.row_base = P.y_pad;
+      E.cs = (uint32_t)P.y_tp * 8u; E.cs2 = 2u * E.cs;
+      E.scale = P.scale; E.do_scale = P.scale != 1.f;
+    }
+    const int nacc = P.nacc, S = P.S;
+    const uint32_t acc_cols = (uint32_t)(P.S * P.NB);
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + P.colC;
+    const bool has_r1 = P.res1 != nullptr, has_r2 = P.res2 != nullptr;
+    // the tile that holds row T - 1: global segment (T - 1) / RL -> item group, tile within the segment
+    const bool zero_pads = P.zero_pads != 0;
+    const int zl_gs = (P.T - 1) / P.RL, zl_grp = zl_gs / S, zl_n = ((P.T - 1) - zl_gs * P.RL) >> 7;
     Ring cr;
     uint32_t tile = 0;
     long long dbg_ew = 0, dbg_eb = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
       __nv_bfloat16* yb = P.y + (int64_t)it.b * P.y_bstride;
-      const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)it.b * P.y_bstride : nullptr;
-      const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)it.b * P.y_bstride : nullptr;
-      for (int n = 0; n < (it.nblk >> 2); ++n, ++tile) {
-        // one warp polls the mbarrier, the other seven park on a named barrier (no issue slots: the SM is issue-bound)
-        if (warp == kWEpi0) { DBG_T0(); tc_wait<64>(&c_full[cr.s], cr.ph, 17); DBG_ADD(dbg_ew); }
-        named_bar_sync(3, 256);
-        if (q == 0 && set == 0) TCF_TRACE(9, tile + 96);
-        tc_fence_after();
-        DBG_T0();
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + P.colC + (uint32_t)(cr.s * P.S * P.NB);
-        if (r2) epilogue_slices<true, true>(P, it, n, r, f0, f1, yb, r1, r2, bias_s, tbase);
-        else if (r1) epilogue_slices<true, false>(P, it, n, r, f0, f1, yb, r1, nullptr, bias_s, tbase);
-        else epilogue_slices<false, false>(P, it, n, r, f0, f1, yb, nullptr, nullptr, bias_s, tbase);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c_free[cr.s]);
-        if (q == 0 && set == 0) TCF_TRACE(10, tile + 96);
-        cr.next(P.nacc);
-        if (P.zero_pads) {
-          // rows [-pad, 0) by the first tile of the utterance, [T, T + pad) by the tile that holds row T - 1 (256 threads)
-          const uint4 z = make_uint4(0, 0, 0, 0);
-          const int et = set * 128 + r;
-          for (int sg = 0; sg < P.S; ++sg) {
-            const int r0 = seg_r0(P, it, sg);
-            if (r0 >= P.T) break;
-            const int q0 = r0 + 128 * n;
-            if (q0 == 0)
-              for (int i = et; i < P.y_chunks * P.y_pad; i += 256)
+      const __nv_bfloat16* r1 = has_r1 ? P.res1 + (int64_t)it.b * P.y_bstride : nullptr;
+      const __nv_bfloat16* r2 = has_r2 ? P.res2 + (int64_t)it.b * P.y_bstride : nullptr;
+      const int seg_t0 = seg_r0(P, it, E.sg0);
+      const int ntile = it.nblk >> 2;
+      for (int n = 0; n < ntile; ++n, ++tile) {
+        {
+          // one warp polls the mbarrier, the other seven park on a named barrier (no issue slots: the SM is issue-bound)
+          if (warp == kWEpi0) {
+            DBG_T0(); tc_wait<64>(&c_full[cr.s], cr.ph, 17); DBG_ADD(dbg_ew);
+          }
+          named_bar_sync(3, 256);
+          if (q == 0 && set == 0) TCF_TRACE(9, tile + 96);
+          tc_fence_after();
+          DBG_T0();
+          const uint32_t tbase = tq + (uint32_t)cr.s * acc_cols;
+          const int t_in_seg = 128 * n + r;
+          if (has_r2) epilogue_tile<true, true>(E, seg_t0, t_in_seg, yb, r1, r2, bias_s, tbase);
+          else if (has_r1) epilogue_tile<true, false>(E, seg_t0, t_in_seg, yb, r1, nullptr, bias_s, tbase);
+          else epilogue_tile<false, false>(E, seg_t0, t_in_seg, yb, nullptr, nullptr, bias_s, tbase);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_free[cr.s]);
+          if (q == 0 && set == 0) TCF_TRACE(10, tile + 96);
+          if ((has_r1 || has_r2) && n + 1 < ntile) {
+            // pull this warp's residual vectors of the NEXT tile towards L2, so that the one-slice-ahead register prefetch of
+            // the slices only has to cover an L2 hit
+            int sl = E.sl0, r0 = seg_t0;
+            for (int i = 0; i < E.cnt; ++i) {
+              const int t = r0 + t_in_seg + 128;
+              if (r0 < E.T && t < E.T) {
+                const uint32_t off = (uint32_t)(E.row_base + t) * 8u + (uint32_t)sl * E.cs2;
+                if (has_r1) { asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + off)); asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + off + E.cs)); }
+                if (has_r2) { asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + off)); asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + off + E.cs)); }
+              }
+              if (++sl == E.nsl) { sl = 0; r0 += E.RL; }
+            }
+          }
+          if (zero_pads && ((it.grp == 0 && n == 0) || (it.grp == zl_grp && n == zl_n))) {
+            // rows [-pad, 0) by the first tile of the utterance, [T, T + pad) by the tile that holds row T - 1
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            const int et = set * 128 + r, nth = 256;
+            const int npad = P.y_chunks * P.y_pad;
+            if (it.grp == 0 && n == 0)
+              for (int i = et; i < npad; i += nth)
                 *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + (i % P.y_pad)) * 8) = z;
-            if (q0 < P.T && q0 + 128 >= P.T)
-              for (int i = et; i < P.y_chunks * P.y_pad; i += 256)
+            if (it.grp == zl_grp && n == zl_n)
+              for (int i = et; i < npad; i += nth)
                 *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + P.y_pad + P.T + (i % P.y_pad)) * 8) = z;
           }
+          DBG_ADD(dbg_eb);
         }
-        DBG_ADD(dbg_eb);
+        cr.next(nacc);
       }
     }
     if (P.dbg && threadIdx.x == kWEpi0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[12] = dbg_ew; d[14] = dbg_eb; }
