@@ -720,30 +720,42 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     // ===================== store: Y (fp32, TMEM; lane = channel) -> bf16 -> conv A stage(s) in shared memory ===============
     // 6 warps: TMEM lane quarter q = warp % 4 (0..2), 16-step half h of every block.  tcgen05.ld.16x256b returns the mma
     // C-fragment layout, which is what stmatrix.trans needs to write 8 channels x 8 time steps as eight 16-byte rows.
+    // (issue-bound SM: all addresses are 32-bit shared-memory offsets precomputed per lane, one polling warp for the group)
     const int q = warp & 3, h = (warp >> 2) & 1;
-    const uint32_t tqa = tmem_base + ((uint32_t)(q * 32) << 16) + P.colY + (uint32_t)h * 16u;
+    const uint32_t colY = P.colY;
+    const uint32_t tqa = tmem_base + ((uint32_t)(q * 32) << 16) + colY + (uint32_t)h * 16u;
     const uint32_t tqb = tqa + (16u << 16);
+    const int LH = P.LH, SR = P.SR, nas = P.nas, ny = P.ny;
     const int slotA = 4 * q + ((lane >> 3) & 1);                       // this lane's stmatrix row: chunk-slot (+2 for the second store)
     const int rowin = 16 * h + (lane >> 4) * 8 + (lane & 7);           // ... and row within the block
-    uint8_t* const mydump = dump + lane * 16;
-    const int LH = P.LH, SR = P.SR;
+    const uint32_t stage0 = smem_u32(asm_), stage_bytes = P.a_stage_bytes;
+    const uint32_t lane_off = (uint32_t)(slotA * SR + rowin) * 16u;    // byte offset of this lane's row in a stage (block at row 0)
+    const uint32_t pair_off = (uint32_t)(2 * SR) * 16u;                // second store: chunk-slot + 2
+    const uint32_t dump_a = smem_u32(dump) + (uint32_t)lane * 16u;
+    // halo copies: last LH rows of block 4n - 1 -> rows [0, LH) of tile n; first LH rows of block 4n + 4 -> rows [128 + LH, SR)
+    const bool ok_next = rowin >= 32 - LH, any_next = 16 * h + 16 > 32 - LH;
+    const bool ok_prev = rowin < LH, any_prev = 16 * h < LH;
+    const uint32_t main_off = lane_off + (uint32_t)LH * 16u;
+    const uint32_t next_off = ok_next ? lane_off + (uint32_t)(LH - 32) * 16u : 0u;      // (only used when ok_next)
+    const uint32_t prev_off = lane_off + (uint32_t)(128 + LH) * 16u;
     Ring yr, open, mainr, closer;
     uint32_t tr_j = 0;
     long long dbg_ty = 0, dbg_tf = 0;
-    auto put = [&](uint8_t* stage, int row0, int vlo, int vhi, const uint32_t (&pa)[4], const uint32_t (&pb)[4]) {
-      // rows [vlo, vhi) of the block go to stage rows row0 + rowin; the other matrices of the store go to the dump
-      if (16 * h >= vhi || 16 * h + 16 <= vlo || TCF_DRY(32)) return;
-      const bool ok = rowin >= vlo && rowin < vhi;
-      uint8_t* a = ok ? stage + ((size_t)slotA * SR + row0 + rowin) * 16 : mydump;
-      uint8_t* b = ok ? a + (size_t)2 * SR * 16 : mydump;
-      stmatrix_x4_trans(a, pa[0], pa[1], pa[2], pa[3]);
-      stmatrix_x4_trans(b, pb[0], pb[1], pb[2], pb[3]);
+    auto stsm2 = [&](uint32_t a, const uint32_t (&pa)[4], const uint32_t (&pb)[4]) {
+      asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(pa[0]), "r"(pa[1]), "r"(pa[2]), "r"(pa[3]) : "memory");
+      asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(a + pair_off), "r"(pb[0]), "r"(pb[1]), "r"(pb[2]), "r"(pb[3]) : "memory");
+    };
+    auto stsm2_masked = [&](bool ok, uint32_t a, const uint32_t (&pa)[4], const uint32_t (&pb)[4]) {
+      // lanes whose matrix is not wanted write it to the dump
+      asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(ok ? a : dump_a), "r"(pa[0]), "r"(pa[1]), "r"(pa[2]), "r"(pa[3]) : "memory");
+      asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(ok ? a + pair_off : dump_a), "r"(pb[0]), "r"(pb[1]), "r"(pb[2]), "r"(pb[3]) : "memory");
     };
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
-      for (int j = -1; j <= it.nblk; ++j) {
+      const int nblk = it.nblk;
+      for (int j = -1; j <= nblk; ++j) {
         const int p = j & 3;
-        const bool opens = p == 3 && j + 1 < it.nblk;                  // first rows of tile (j + 1) / 4's stage
+        const bool opens = p == 3 && j + 1 < nblk;                     // first rows of tile (j + 1) / 4's stage
         if (warp == kWStore0) {                                        // one polling warp per role group
           { DBG_T0(); tc_wait<0>(&y_full[yr.s], yr.ph, 15); DBG_ADD(dbg_ty); }
           if (opens) { DBG_T0(); tc_wait<0>(&as_free[open.s], open.ph ^ 1, 16); DBG_ADD(dbg_tf); }
@@ -758,27 +770,26 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&y_free[yr.s]);
-        yr.next(P.ny);
+        yr.next(ny);
         uint32_t pa[4], pb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           pa[i] = cvt_bf16x2(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
           pb[i] = cvt_bf16x2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]));
         }
-        if (j >= 0 && j < it.nblk)
-          put(asm_ + (size_t)mainr.s * P.a_stage_bytes, LH + 32 * p, 0, 32, pa, pb);
-        if (opens) {
-          put(asm_ + (size_t)open.s * P.a_stage_bytes, LH - 32, 32 - LH, 32, pa, pb);
-          open.next(P.nas);
+        if (!TCF_DRY(32)) {
+          if (j >= 0 && j < nblk) stsm2(stage0 + (uint32_t)mainr.s * stage_bytes + main_off + (uint32_t)p * 512u, pa, pb);
+          if (opens && any_next) stsm2_masked(ok_next, stage0 + (uint32_t)open.s * stage_bytes + next_off, pa, pb);
+          if (p == 0 && j > 0 && any_prev) stsm2_masked(ok_prev, stage0 + (uint32_t)closer.s * stage_bytes + prev_off, pa, pb);
         }
-        if (p == 0 && j > 0) {                                         // last rows of tile j / 4 - 1: the stage is complete
-          put(asm_ + (size_t)closer.s * P.a_stage_bytes, 128 + LH, 0, LH, pa, pb);
+        if (opens) open.next(nas);
+        if (p == 0 && j > 0) {                                         // tile j / 4 - 1 is complete
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(tile_edge(P, it, (j >> 2) - 1) ? &as_edone[closer.s] : &as_done[closer.s]);
-          closer.next(P.nas);
+          closer.next(nas);
         }
-        if (p == 3 && j >= 0) mainr.next(P.nas);
+        if (p == 3 && j >= 0) mainr.next(nas);
         if (warp == kWStore0) TCF_TRACE(6, tr_j);
         ++tr_j;
       }
