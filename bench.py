@@ -175,6 +175,10 @@ def act1d_sweep(pkg, torch, dev, pk):
                 out["op_boundary"].append({"C": Cn, "T": T, "B": Bn, "dtype": name, "precise": precise, "ms": ms,
                                            "GBps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
             del x
+    # the "existing GPU kernel to beat" (BASELINE.md section 4): the reference's own fused CUDA op
+    # (alias_free_activation/cuda/anti_alias_activation_cuda.cu:43-181) built for sm_100 by baseline/build_ref_kernel.py,
+    # on the same shapes and tensors.  Bench-only: nothing in the product imports it.
+    out["reference_cuda_kernel"] = ref_kernel_times(torch, dev, pk, timed)
     st = torch.cuda.current_stream().cuda_stream
     for Cn, T, Bn in ((768, 940, 32), (384, 3760, 32), (192, 15040, 32), (96, 60160, 32), (24, 240640, 32)):
         x = (torch.randn(Bn, Cn, T, device=dev) * 1.5).to(torch.bfloat16)
@@ -193,6 +197,33 @@ def act1d_sweep(pkg, torch, dev, pk):
             out["c8t_bf16"].append({"C": Cn, "T": T, "B": Bn, "impl": name, "ms": ms, "GBps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
         del x, y
     return out
+
+
+def ref_kernel_times(torch, dev, pk, timed):
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import build_ref_kernel
+        mod = build_ref_kernel.load()
+    except Exception as e:                                      # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    if mod is None:
+        return {"unavailable": "baseline/_ref/anti_alias_activation_cuda not built (python baseline/build_ref_kernel.py)"}
+    from oracle import bigvgan_oracle as O
+    taps = torch.tensor(O.act1d_taps(), dtype=torch.float32, device=dev).view(1, 1, 12)
+    rows = []
+    for Cn, T, Bn in ((768, 4096, 44), (96, 65536, 22), (24, 1048576, 6)):
+        a = torch.randn(Cn, device=dev) * 0.5
+        b = torch.randn(Cn, device=dev) * 0.5
+        for dt, name, es in ((torch.float32, "fp32", 4), (torch.bfloat16, "bf16", 2)):
+            x = torch.randn(Bn, Cn, T, device=dev).to(dt)
+            try:
+                ms = timed(lambda: mod.forward(x, taps, taps, a, b))
+                gbs = 2.0 * Bn * Cn * T * es / (ms * 1e-3) / 1e9
+                rows.append({"C": Cn, "T": T, "B": Bn, "dtype": name, "ms": ms, "GBps": gbs, "frac_of_hbm": gbs / pk["hbm"]})
+            except Exception as e:                              # noqa: BLE001
+                rows.append({"C": Cn, "T": T, "B": Bn, "dtype": name, "error": f"{type(e).__name__}: {e}"})
+            del x
+    return {"kernel": "reference anti_alias_activation_cuda.forward, -gencode arch=compute_100,code=sm_100", "rows": rows}
 
 
 def latency_b1(m, O, h, torch, dev):
@@ -394,11 +425,13 @@ def run_ours(args):
             print(f"bench: warning: {fus_n} fused launches, accounting expects {work['fused_launches']}", file=sys.stderr)
         if dom == "actconv":
             # algorithmic bytes per launch / average launch time; traffic = ncu dram bytes per launch (same step)
-            roof = {"kernel": "conv_umma_fused_kernel (Activation1d -> Conv1d, narrow stages)", "bound": "hbm",
+            roof = {"kernel": "fused Activation1d -> Conv1d of the narrow stages: actconv_tc_kernel (tensor-core FIRs, C = 96 / 48) + "
+                              "conv_umma_fused_kernel (C = 24)", "bound": "hbm",
                     "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": fus_gbs / pk["hbm"],
                     "traffic": measured_traffic("actconv")[0], "algorithmic_bytes_per_launch": work["fused_bytes"] / max(fus_n, 1),
                     "traffic_note": measured_traffic("actconv")[1],
-                    "limiter": "FMA pipe (the 12+12-tap FIR stencil), not HBM: see profiles/README.md"}
+                    "limiter": "instruction issue of the snake / store / epilogue warps (actconv_tc_kernel) and the FMA pipe "
+                               "(conv_umma_fused_kernel), not HBM: see profiles/README.md"}
         elif dom == "act1d":
             roof = {"kernel": "act1d_c8t_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": act_gbs / pk["hbm"], "traffic": None}

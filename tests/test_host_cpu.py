@@ -148,3 +148,30 @@ def test_decode_ragged_grouping_logic(P):
     assert m.decode_ragged([], mels) == []
     with pytest.raises(RuntimeError):
         m.decode_ragged(lats, mels[:2])
+
+
+def test_tc_kernels_issue_mma_from_uniform_registers():
+    """actconv_tc_kernel's speed depends on ptxas proving the tcgen05.mma operands warp-uniform (uniform-datapath issue, ~10
+    instructions per MMA); when it cannot, every MMA goes through an ELECT / R2UR.BROADCAST loop and the kernel runs 2x
+    slower (profiles/README.md, round 2).  Unrelated code changes have flipped this, so the built library is checked."""
+    import re
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    import index_tts_ipex_b200 as pkg
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.build.lib_path()], stdout=subprocess.PIPE, text=True, check=True).stdout
+    cur, counts = None, {}
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = [0, 0]
+        elif cur:
+            counts[cur][0] += len(re.findall(r"\bUTC\w*MMA", line))
+            counts[cur][1] += len(re.findall(r"\bR2UR\.BROADCAST", line))
+    for name in ("actconv_tc_kernel", "act1d_tc_kernel"):
+        k = [v for n, v in counts.items() if name in n]
+        assert k and k[0][0] >= 6, (name, k)
+        assert k[0][1] <= 8, f"{name}: {k[0][1]} R2UR.BROADCAST -- the MMA issue loops fell off the uniform datapath"

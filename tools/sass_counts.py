@@ -14,7 +14,10 @@ pats = collections.OrderedDict([("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("LDT
                                 ("UBLKCP (cp.async.bulk)", r"\bUBLKCP"), ("UTMALDG/STG (tensor TMA)", r"\bUTMA(LDG|STG)"),
                                 ("UBLKPF (bulk L2 prefetch)", r"\bUBLKPF"), ("STSM (stmatrix)", r"\bSTSM"), ("SYNCS (mbarrier)", r"\bSYNCS"),
                                 ("FFMA2/FMUL2/FADD2", r"\bF(FMA|MUL|ADD)2\b"), ("MUFU", r"\bMUFU"), ("HMMA (legacy mma.sync)", r"\bHMMA"),
-                                ("USETMAXREG", r"\bUSETMAXREG")])
+                                ("USETMAXREG", r"\bUSETMAXREG"),
+                                # a tcgen05.mma whose operands ptxas could not prove warp-uniform is issued through an
+                                # ELECT / R2UR.BROADCAST loop (~150 cycles per MMA instead of ~10): must stay at a handful
+                                ("R2UR.BROADCAST", r"\bR2UR\.BROADCAST")])
 cur, counts, sizes = None, collections.OrderedDict(), {}
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
