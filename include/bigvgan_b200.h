@@ -184,6 +184,16 @@ BVG_API int bvg_plan_finalize(bvg_plan* plan, int enable_bf16_umma);
  * bf16 splits, fast-math Activation1d) */
 BVG_API size_t bvg_workspace_bytes(const bvg_plan* plan, int64_t B, int64_t T0, int64_t Tm, int dtype);
 
+/* Reference-mel front end.   replaces  MelSpectrogramFeatures.forward  (indextts/utils/feature_extractors.py:24-50, called
+ * from infer.py:82-93): torchaudio MelSpectrogram(n_fft, hop, periodic hann, center + reflect pad, power 1, htk mel scale)
+ * + safe_log(clip 1e-7) (utils/common.py:110).
+ *   audio [B, L] fp32 device (mono, already at the model's sample rate), fb [n_fft/2+1, n_mels] fp32 device = the mel
+ *   filterbank (torchaudio.functional.melscale_fbanks; the host layer computes it), mel [B, bvg_mel_frames(L, hop), n_mels]
+ *   fp32 device -- the layout bvg_speaker_embed / bvg_decode take (the reference's [B, n_mels, frames] transposed). */
+BVG_API int64_t bvg_mel_frames(int64_t L, int hop);
+BVG_API int bvg_mel_frontend(float* mel, const float* audio, const float* fb, int64_t B, int64_t L, int n_fft, int hop,
+                             int n_mels, void* stream);
+
 /* speaker encoder only:  mel [Bm, Tm, num_mels] fp32 device -> spk [Bm, emb] fp32 device
  * (ECAPA_TDNN.forward, ECAPA_TDNN.py:543-581, lengths=None) */
 BVG_API int bvg_speaker_embed(const bvg_plan* plan, const float* mel, int64_t Bm, int64_t Tm,

@@ -48,6 +48,8 @@ SIGNATURES = {
     "bvg_debug_set_umma_counters": (None, [_vp]),
     "bvg_actconv_umma_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "bvg_actconv_impl_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
+    "bvg_mel_frames": (_i64, [_i64, _int]),
+    "bvg_mel_frontend": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp]),
     "bvg_conv1d_umma_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "bvg_convtr1d_umma_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "bvg_plan_create": (_int, [C.POINTER(_vp), C.POINTER(BvgConfig)]),

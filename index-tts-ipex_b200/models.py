@@ -323,6 +323,34 @@ class BigVGAN(nn.Module):
         return spk
 
     @torch.no_grad()
+    def voice_embedding(self, mel_ref: torch.Tensor = None, audio: torch.Tensor = None, key=None, cache=None) -> torch.Tensor:
+        """Speaker embedding [B',1,emb] of a voice prompt, cached per voice.  Pass the prompt either as
+        `mel_ref` [B',Tm,num_mels] or as 24 kHz mono `audio` [B',L] (then the mel front end of mel.py runs first, as
+        infer.py:82-93 does); `key` names the voice (default: a digest of the prompt); `cache` defaults to the model's own
+        SpeakerEmbeddingCache.  The result goes to decode(..., spk=...) and removes the speaker encoder from steady state."""
+        from .mel import MelSpectrogramFeatures, SpeakerEmbeddingCache
+        if (mel_ref is None) == (audio is None):
+            raise ValueError("pass exactly one of mel_ref / audio")
+        if cache is None:
+            if not hasattr(self, "_spk_cache"):
+                self._spk_cache = SpeakerEmbeddingCache()
+            cache = self._spk_cache
+        src = mel_ref if mel_ref is not None else audio
+        if key is None:
+            key = SpeakerEmbeddingCache.digest(src)
+        key = (key, str(src.device))
+        emb = cache.get(key)
+        if emb is None:
+            cache.misses += 1
+            if mel_ref is None:
+                if not hasattr(self, "_mel_frontend"):
+                    self._mel_frontend = MelSpectrogramFeatures(n_mels=int(self.h.num_mels))
+                mel_ref = self._mel_frontend.forward_btc(audio)
+            emb = self.speaker_embed(mel_ref)
+            cache.put(key, emb)
+        return emb
+
+    @torch.no_grad()
     def decode(self, x, mel_ref=None, spk=None, pcm16=False, halo=(0, 0), workspace=None):
         """The device-resident call.  x [B,T0,gpt_dim]; exactly one of mel_ref [B',Tm,num_mels] /
         spk [B',1,emb].  Returns wav fp32 [B,1,L] (or int16 [B,L] when pcm16=True, the fused
