@@ -213,6 +213,13 @@ BVG_API int bvg_decode(const bvg_plan* plan, const float* latent, const float* m
                float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* bvg_decode with the latent in the dtype the GPT hands it over in (gpt/model.py:462-477 under the autocast of infer.py:194):
+ * latent [B, T0, gpt_dim] channels-last, latent_dtype in {BVG_F32, BVG_BF16, BVG_F16}.  The bf16 path ingests it directly
+ * (no fp32 round trip); the fp32 paths widen it once in the workspace.  Everything else as bvg_decode. */
+BVG_API int bvg_decode_lat(const bvg_plan* plan, const void* latent, int latent_dtype, const float* mel, const float* spk,
+                   int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16,
+                   int64_t t_lo_pad, int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers: copies latent/mel host->device, decodes, copies the waveform
  * back (the end-to-end figure bench.py reports as `e2e`).  Uses the plan's device and the
  * given stream; synchronises the stream before returning.  latent/mel/wav should be pinned. */

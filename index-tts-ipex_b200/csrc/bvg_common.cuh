@@ -141,6 +141,8 @@ int repack_conv_weight_launch(float* dst, const float* src, int64_t Cout, int64_
 
 
 // ---- small kernels (misc.cu) ------------------------------------------------------------------
+// dst[i] = float(src[i]) for bf16 / fp16 sources
+int cast_to_f32_launch(float* dst, const void* src, int src_dtype, int64_t n, cudaStream_t st);
 // y[b,co] = epilogue(sum_ci w[ci][co] x[b,ci]) for contiguous x [B,Cin], y [B,Cout]; w is the K=1 [Cin][Cout] pack
 int matvec_launch(float* y, const float* x, const float* w_ic, const ConvEpilogue& ep, int64_t B, int Cin, int Cout,
                   cudaStream_t st);

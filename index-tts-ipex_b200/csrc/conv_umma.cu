@@ -677,6 +677,8 @@ int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64
     to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
   else if (src_dtype == BVG_BF16)
     to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+  else if (src_dtype == BVG_F16)
+    to_c8t_kernel<__half><<<grid, 256, 0, st>>>(dst.p, (const __half*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
   else { set_error("to_c8t: unsupported dtype"); return BVG_ERR_INVALID; }
   BVG_LAUNCHED();
   return BVG_OK;

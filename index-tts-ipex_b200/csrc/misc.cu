@@ -214,4 +214,22 @@ int conv_post_launch(float* wav, int16_t* pcm, const void* x, const float* w, co
   return BVG_OK;
 }
 
+namespace {
+template <typename TS>
+__global__ void cast_to_f32_kernel(float* __restrict__ dst, const TS* __restrict__ src, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = to_f<TS>(src[i]);
+}
+}  // namespace
+
+int cast_to_f32_launch(float* dst, const void* src, int src_dtype, int64_t n, cudaStream_t st) {
+  if (n == 0) return BVG_OK;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  ProfScope prof(st, KC_OTHER);
+  if (src_dtype == BVG_BF16) cast_to_f32_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(dst, (const __nv_bfloat16*)src, n);
+  else if (src_dtype == BVG_F16) cast_to_f32_kernel<__half><<<blocks, 256, 0, st>>>(dst, (const __half*)src, n);
+  else { set_error("cast_to_f32: unsupported dtype"); return BVG_ERR_INVALID; }
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
 }  // namespace bvg

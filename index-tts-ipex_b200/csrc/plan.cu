@@ -497,12 +497,14 @@ UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1
 }
 
 // The bf16 throughput path: c8t activations, tcgen05 convs (models.py:220-248).
-int decode_bf16_umma(const bvg_plan* P, const float* latent, const GenWs& g, int64_t B, int64_t T0, int64_t Bm,
+int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, const GenWs& g, int64_t B, int64_t T0, int64_t Bm,
                      float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st) {
   const bvg_config& c = P->cfg;
   // latent [B,T0,gpt_dim] fp32 (channels-last) -> c8t bf16
   C8T lat = make_c8t(g.T1, c.gpt_dim, (int)T0);
-  BVG_TRY(to_c8t_launch(lat, latent, T0 * c.gpt_dim, 1, c.gpt_dim, BVG_F32, B, st));
+  // (the GPT hands its latent over in its autocast dtype, gpt/model.py:462-477 under infer.py:194: fp16 / bf16 / fp32 are
+  // all ingested directly, [B, T, C] channels-last, no fp32 round trip)
+  BVG_TRY(to_c8t_launch(lat, latent, T0 * c.gpt_dim, 1, c.gpt_dim, latent_dtype, B, st));
   int64_t T = T0;
   C8T xs = make_c8t(g.XS, P->C[0], (int)T);
   {
@@ -923,7 +925,17 @@ int bvg_speaker_embed(const bvg_plan* P, const float* mel, int64_t Bm, int64_t T
 int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const float* spk_in, int64_t B, int64_t T0,
                int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad,
                void* workspace, size_t workspace_bytes, void* stream) {
+  return bvg_decode_lat(P, latent, BVG_F32, mel, spk_in, B, T0, Bm, Tm, dtype, wav, pcm16, t_lo_pad, t_hi_pad, workspace,
+                        workspace_bytes, stream);
+}
+
+int bvg_decode_lat(const bvg_plan* P, const void* latent_any, int latent_dtype, const float* mel, const float* spk_in, int64_t B,
+                   int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16, int64_t t_lo_pad,
+                   int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  BVG_CHECK_ARG(latent_dtype == BVG_F32 || latent_dtype == BVG_BF16 || latent_dtype == BVG_F16,
+                "decode: latent dtype must be BVG_F32, BVG_BF16 or BVG_F16");
+  const float* latent = static_cast<const float*>(latent_any);
   BVG_CHECK_ARG(P && latent && workspace, "decode: null argument");
   if (!P->finalized) { set_error("decode: plan not finalised"); return BVG_ERR_STATE; }
   BVG_CHECK_ARG((mel != nullptr) != (spk_in != nullptr), "decode: pass exactly one of mel / spk");
@@ -957,7 +969,12 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
         BVG_TRY(conv_f32(g.cond[i + 1], P->C[i + 1], spk, nullptr, E, 1, 1, P->conds[i], ep, Bm, 1, 1, 0, st));
   }
   if (dtype == BVG_BF16 && P->umma)
-    return decode_bf16_umma(P, latent, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st);
+    return decode_bf16_umma(P, latent_any, latent_dtype, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st);
+  if (latent_dtype != BVG_F32) {
+    // the fp32 paths read the latent through the CUDA-core conv: widen it once into the staging buffer
+    BVG_TRY(cast_to_f32_launch(g.latent_dev, latent_any, latent_dtype, B * T0 * c.gpt_dim, st));
+    latent = g.latent_dev;
+  }
   // BVG_F32X3: the fp32 path below with the Conv1d layers on the tensor cores (3-term bf16 split); everything else
   // (Activation1d with libdevice sinf, ConvTranspose1d, speaker encoder, conv_post) is the fp32 CUDA-core code
   void* x3 = g.X3;

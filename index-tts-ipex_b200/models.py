@@ -360,7 +360,12 @@ class BigVGAN(nn.Module):
             raise RuntimeError(f"expected latent [B, T0, {int(self.h.gpt_dim)}], got {tuple(x.shape)}")
         if (mel_ref is None) == (spk is None):
             raise RuntimeError("pass exactly one of mel_ref / spk")
-        lat = x.detach().to(torch.float32).contiguous()
+        # the GPT hands the latent over in its autocast dtype (gpt/model.py:462-477 under infer.py:194): fp16 / bf16 / fp32
+        # [B, T, C] tensors are ingested as they are, anything else is widened to fp32 first
+        lat_code = {torch.float32: capi.BVG_F32, torch.bfloat16: capi.BVG_BF16, torch.float16: capi.BVG_F16}.get(x.dtype)
+        lat = x.detach().contiguous() if lat_code is not None else x.detach().to(torch.float32).contiguous()
+        if lat_code is None:
+            lat_code = capi.BVG_F32
         dev = lat.device
         plan = self._ensure_plan(dev)
         B, T0, _ = lat.shape
@@ -389,8 +394,8 @@ class BigVGAN(nn.Module):
             wav_ptr, pcm_ptr = out.data_ptr(), None
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
-            capi.check(capi.lib().bvg_decode(plan, lat.data_ptr(), mel_ptr, spk_ptr, B, T0, Bm, Tm, code, wav_ptr,
-                                             pcm_ptr, lo, hi, ws.data_ptr(), ws.numel(), st), "bvg_decode")
+            capi.check(capi.lib().bvg_decode_lat(plan, lat.data_ptr(), lat_code, mel_ptr, spk_ptr, B, T0, Bm, Tm, code, wav_ptr,
+                                                 pcm_ptr, lo, hi, ws.data_ptr(), ws.numel(), st), "bvg_decode_lat")
         return out
 
     def forward(self, x, mel_ref, lens=None):

@@ -293,3 +293,23 @@ def test_snake_activation_config(P, precision):
         assert float((y - ref).abs().max()) <= 2e-5
     else:
         assert O.snr_db(ref, y) >= BF16_SNR_GATE
+
+
+# ------------------------------------------------------------------ latent hand-off in the GPT's dtype
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_latent_handoff_dtypes(P, prec):
+    """decode() ingests fp16 / bf16 latents directly ([B, T, C], gpt/model.py:462-477 under the autocast of infer.py:194):
+    the result must be bit-identical to decoding the same values widened to fp32 by the caller."""
+    h = O.small_config()
+    m = P.BigVGAN(h, use_cuda_kernel=True)
+    m.load_state_dict(O.make_state_dict(h, 0, "wild"), strict=True)
+    m = m.cuda().eval()
+    m.remove_weight_norm()
+    m.precision = prec
+    lat, mel = O.synthetic_inputs(h, 2, 40, 8, seed=5)
+    lat, mel = lat.cuda(), mel.cuda()
+    for dt in (torch.float16, torch.bfloat16):
+        lo = lat.to(dt)
+        a = m.decode(lo, mel_ref=mel)
+        b = m.decode(lo.float(), mel_ref=mel)
+        assert torch.equal(a, b), (prec, dt, float((a - b).abs().max()))
