@@ -220,6 +220,16 @@ BVG_API int bvg_decode_lat(const bvg_plan* plan, const void* latent, int latent_
                    int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16,
                    int64_t t_lo_pad, int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Ragged batch: true batched vocoding of utterances of DIFFERENT lengths in one call (what infer_fast lacks,
+ * infer.py:480-503: it concatenates sentences along time instead).  latent [B, T0_max, gpt_dim] (rows past an utterance's
+ * length are ignored), lens_dev = device int32 [B] latent-frame counts (1 <= lens[b] <= T0_max).  bf16 path only.
+ * Every kernel clips its tiles and applies its edge semantics (zero / replicate padding) at each utterance's own length, so
+ * utterance b's samples [0, lens[b] * prod(rates)) equal those of decoding it alone through the same kernels; the rest of
+ * its row in wav / pcm16 ([B, T0_max * prod(rates)]) is zero. */
+BVG_API int bvg_decode_varlen(const bvg_plan* plan, const void* latent, int latent_dtype, const int32_t* lens_dev,
+                      const float* mel, const float* spk, int64_t B, int64_t T0_max, int64_t Bm, int64_t Tm,
+                      float* wav, int16_t* pcm16, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers: copies latent/mel host->device, decodes, copies the waveform
  * back (the end-to-end figure bench.py reports as `e2e`).  Uses the plan's device and the
  * given stream; synchronises the stream before returning.  latent/mel/wav should be pinned. */

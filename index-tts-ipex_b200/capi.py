@@ -60,6 +60,7 @@ SIGNATURES = {
     "bvg_speaker_embed": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, C.c_size_t, _vp]),
     "bvg_decode": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _i64, _vp, C.c_size_t, _vp]),
     "bvg_decode_lat": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _i64, _i64, _vp, C.c_size_t, _vp]),
+    "bvg_decode_varlen": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "bvg_decode_host": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _vp, _vp, _vp, C.c_size_t, _vp]),
 }
 

@@ -24,7 +24,8 @@ template <int NCH>
 __global__ void __launch_bounds__(256, 3)
 act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                  const float* __restrict__ alpha_log, const float* __restrict__ beta_log, int C, int chunks, int T,
-                 int Tp, int pad) {
+                 int Tp, int pad, const int* __restrict__ lens, int len_mul) {
+  if (lens) T = lens[blockIdx.z] * len_mul;                       // ragged batch: this utterance's own length
   constexpr int V = 16;
   constexpr int RGW = 8 / NCH;            // row groups per warp
   constexpr int TR = 8 * RGW * V;         // rows per CTA (128 / 256 / 512)
@@ -133,14 +134,19 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
 __global__ void __launch_bounds__(256)
 conv_post_c8t_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ w, const float* __restrict__ bias, int Cin, int chunks, int T, int Tp,
-                     int pad, int K, int64_t s_lo, int64_t s_hi) {
+                     int pad, int K, int64_t s_lo, int64_t s_hi, const int* __restrict__ lens, int len_mul) {
   extern __shared__ float wsm[];   // [Cin*K] as [ci][k]
   for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int64_t Tout = T - s_lo - s_hi;
+  const int64_t Tout = T - s_lo - s_hi;                             // row pitch of the output (longest utterance)
   const int64_t to = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (to >= Tout) return;
+  if (lens && to + s_lo >= (int64_t)lens[b] * len_mul - s_hi) {     // ragged batch: samples past this utterance's end are zero
+    if (wav) wav[(int64_t)b * Tout + to] = 0.f;
+    if (pcm) pcm[(int64_t)b * Tout + to] = 0;
+    return;
+  }
   const int64_t t = to + s_lo;
   const int hp = (K - 1) / 2;
   float acc = bias ? bias[0] : 0.f;
@@ -171,7 +177,7 @@ int launch_act(const C8T& y, const C8T& x, const float* a, const float* b_, int6
   BVG_TRY(smem_opt_in(act1d_c8t_kernel<NCH>, opted, (int)smem));
   dim3 grid((unsigned)((x.Tp + TR - 1) / TR), (unsigned)((x.chunks + NCH - 1) / NCH), (unsigned)B);
   ProfScope prof(st, KC_ACT1D);
-  act1d_c8t_kernel<NCH><<<grid, 256, smem, st>>>(y.p, x.p, a, b_, x.C, x.chunks, x.T, x.Tp, x.pad);
+  act1d_c8t_kernel<NCH><<<grid, 256, smem, st>>>(y.p, x.p, a, b_, x.C, x.chunks, x.T, x.Tp, x.pad, x.lens, x.len_mul);
   BVG_LAUNCHED();
   return BVG_OK;
 }
@@ -204,7 +210,7 @@ int conv_post_c8t_launch(float* wav, int16_t* pcm, const C8T& x, const float* w,
   dim3 grid((unsigned)((Tout + 255) / 256), (unsigned)B);
   ProfScope prof(st, KC_OTHER);
   conv_post_c8t_kernel<<<grid, 256, (size_t)x.C * K * 4, st>>>(wav, pcm, x.p, w, bias, x.C, x.chunks, x.T, x.Tp, x.pad, K,
-                                                              s_lo, s_hi);
+                                                              s_lo, s_hi, x.lens, x.len_mul);
   BVG_LAUNCHED();
   return BVG_OK;
 }

@@ -77,11 +77,12 @@ struct ActTcParams {
   int cps, sps, nseg, ntile;      // chunks per tile, lane-chunk slots per segment, segments per item, channel tiles
   int RL, NG;                     // rows per range, range groups per utterance
   int nitems;
+  const int* lens; int len_mul;   // ragged batch: utterance b has lens[b] * len_mul rows (else T)
   long long* dbg;                 // optional [grid][16] per-role cycle counters (bvg_debug_set_umma_counters)
   int dry;                        // BVG_DEBUG builds only: skip parts of the pipeline (bottleneck experiments, garbage results)
 };
 
-struct TcItem { int b, tile, grp, nblk, cps_t; };
+struct TcItem { int b, tile, grp, nblk, cps_t, T; };
 __device__ __forceinline__ TcItem tc_item(const ActTcParams& P, int item) {
   TcItem it;
   const int per_b = P.ntile * P.NG;
@@ -91,7 +92,8 @@ __device__ __forceinline__ TcItem tc_item(const ActTcParams& P, int item) {
   it.grp = r - it.tile * P.NG;
   it.cps_t = min(P.cps, P.chunks - it.tile * P.cps);
   const int tr0 = it.grp * P.nseg * P.RL;                      // segment 0 (the longest of the item)
-  it.nblk = (min(P.T, tr0 + P.RL) - tr0 + kTBlk - 1) / kTBlk;
+  it.T = rows_of(P.lens, P.len_mul, it.b, P.T);
+  it.nblk = max(0, (min(it.T, tr0 + P.RL) - tr0 + kTBlk - 1) / kTBlk);    // 0: the whole item lies past the utterance's end
   return it;
 }
 
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     auto prefetch_stage = [&](const TcItem& pit, int pst) {
       if (!(lane < 16 && ps < P.nseg && pcc < pit.cps_t)) return;
       const int tr0 = (pit.grp * P.nseg + ps) * P.RL;
-      if (tr0 >= P.T) return;
+      if (tr0 >= pit.T) return;
       const int lo = max(tr0 + kTXBlk * kTBlk * pst - 40 + (pst ? 16 : 0), 0);
-      const int hi = min(tr0 + kTXBlk * kTBlk * pst - 40 + kTXRows, P.T);
+      const int hi = min(tr0 + kTXBlk * kTBlk * pst - 40 + kTXRows, pit.T);
       if (hi > lo)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
                      ::"l"(P.x + (int64_t)pit.b * P.bstride + ((int64_t)(pit.tile * P.cps + pcc) * P.Tp + P.pad + lo) * 8),
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     bool first = true;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       const int nstages = (it.nblk + 2 + kTXBlk - 1) / kTXBlk;
       const bool has_next = item + (int)gridDim.x < P.nitems;
       const TcItem nit = has_next ? tc_item(P, item + gridDim.x) : it;
@@ -228,9 +231,9 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
           uint32_t total = 0;
           for (int s = 0; s < P.nseg; ++s) {
             const int tr0 = (it.grp * P.nseg + s) * P.RL;
-            if (tr0 >= P.T) break;
+            if (tr0 >= it.T) break;
             const int ts = tr0 + kTXBlk * kTBlk * st - 40;
-            const int lo = max(ts, 0), hi = min(ts + kTXRows, P.T);
+            const int lo = max(ts, 0), hi = min(ts + kTXRows, it.T);
             if (hi > lo) total += (uint32_t)(hi - lo) * 16u * (uint32_t)it.cps_t;
           }
           mbar_expect_tx(&x_full[xs], total);
@@ -239,8 +242,8 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
         if (lane < 16 && ps < P.nseg && pcc < it.cps_t) {
           const int tr0 = (it.grp * P.nseg + ps) * P.RL;
           const int ts = tr0 + kTXBlk * kTBlk * st - 40;
-          const int lo = max(ts, 0), hi = min(ts + kTXRows, P.T);
-          if (tr0 < P.T && hi > lo)
+          const int lo = max(ts, 0), hi = min(ts + kTXRows, it.T);
+          if (tr0 < it.T && hi > lo)
             bulk_g2s(smem_u32(xsm + xs * kXStageBytes) + (uint32_t)((lane * kTXRows + (lo - ts)) * 16),
                      xb + ((int64_t)(it.tile * P.cps + pcc) * P.Tp + P.pad + lo) * 8, (uint32_t)(hi - lo) * 16u, &x_full[xs]);
         }
@@ -252,16 +255,17 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     int xs = 0; uint32_t xph = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       const int nstages = (it.nblk + 2 + kTXBlk - 1) / kTXBlk;
       for (int st = 0; st < nstages; ++st) {
         mbar_wait_relaxed(&x_full[xs], xph);
         uint4* stage = reinterpret_cast<uint4*>(xsm + xs * kXStageBytes);
         for (int s = 0; s < P.nseg; ++s) {
           const int tr0 = (it.grp * P.nseg + s) * P.RL;
-          if (tr0 >= P.T) break;
+          if (tr0 >= it.T) break;
           const int ts = tr0 + kTXBlk * kTBlk * st - 40;
           const int nlo = min(max(-ts, 0), kTXRows);                 // rows [0, nlo): t < 0
-          const int rhi = min(max(P.T - ts, 0), kTXRows);            // rows [rhi, kTXRows): t >= T
+          const int rhi = min(max(it.T - ts, 0), kTXRows);            // rows [rhi, kTXRows): t >= T
           if (nlo == 0 && rhi == kTXRows) continue;
           for (int cc = 0; cc < it.cps_t; ++cc) {
             uint4* base = stage + (s * P.sps + cc) * kTXRows;
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       const int nup = it.nblk + 2;
       for (int nu = 0; nu < nup; ++nu) {
         // ---- up-FIR of block i = nu - 1: U[ub] = X rows [t0 - 8, t0 + 40) x taps (hi + lo)
@@ -339,6 +344,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     long long dbg_wa = 0, dbg_wy = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       int next_a = -1;                                                 // first block whose activated samples were not awaited yet
       for (int j = 0; j < it.nblk; ++j) {
         // ---- down-FIR of block j: Y[yb] = A ring samples [64 j - 16, 64 j + 80) x taps
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     const long long dbg_sstart = P.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       float sc0 = 0.f, sc1 = 0.f;
       {
         const int ch = (it.tile * P.cps + cc) * 8 + (ln & 7);
@@ -464,6 +471,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     const long long dbg_tstart = P.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+      if (it.nblk <= 0) continue;
       __nv_bfloat16* ybase = P.y + (int64_t)it.b * P.bstride;
       // one block: pack `ca`/`cb` (already requested from TMEM) into rows [32 (j % 4) + 16 h, +16) of the out stage
       auto step = [&](uint32_t (&ca)[8], uint32_t (&cb)[8], uint32_t (&na)[8], uint32_t (&nb)[8], int j, uint8_t* obuf) {
@@ -513,9 +521,9 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
         if (issuer) {
           const int s = sL / P.sps, cc = sL - s * P.sps;
           const int tr0 = (it.grp * P.nseg + s) * P.RL;
-          if (s < P.nseg && cc < it.cps_t && tr0 < P.T) {
+          if (s < P.nseg && cc < it.cps_t && tr0 < it.T) {
             const int row0 = tr0 + 128 * g;
-            const int nrows = min(128, min(P.T, tr0 + P.RL) - row0);
+            const int nrows = min(128, min(it.T, tr0 + P.RL) - row0);
             if (nrows > 0)
               bulk_s2g(ybase + ((int64_t)(it.tile * P.cps + cc) * P.Tp + P.pad + row0) * 8, obuf + (size_t)sL * kTOutPitch * 16,
                        (uint32_t)nrows * 16u);
@@ -543,8 +551,10 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
 // the exact replicate-pad semantics, zero halo rows, zero padding channels.  One warp per (chunk, utterance).
 __global__ void __launch_bounds__(32) act1d_c8t_edge_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
-                                                            int C, int chunks, int T, int Tp, int pad) {
+                                                            int C, int chunks, int T, int Tp, int pad, const int* __restrict__ lens,
+                                                            int len_mul) {
   const int chunk = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  if (lens) T = lens[b] * len_mul;
   const int64_t base = ((int64_t)b * chunks + chunk) * Tp;
   if (lane < 16) {
     constexpr int V = 8;
@@ -583,6 +593,7 @@ int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const fl
   P.x = x.p; P.y = y.p; P.alpha = alpha_log; P.beta = beta_log;
   P.C = x.C; P.chunks = x.chunks; P.T = x.T; P.Tp = x.Tp; P.pad = x.pad;
   P.bstride = x.batch_stride();
+  P.lens = x.lens; P.len_mul = x.len_mul;
   const int ch = x.chunks;
   if (ch % 16 == 0 || ch > 16) { P.cps = 16; P.sps = 16; }
   else if (ch % 8 == 0) { P.cps = 8; P.sps = 8; }
@@ -620,7 +631,7 @@ int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const fl
   BVG_CHECK_ARG(B <= 65535, "act1d_tc: batch too large for the edge pass grid");
   {
     ProfScope prof(st, KC_ACT1D);
-    act1d_c8t_edge_kernel<<<dim3((unsigned)x.chunks, (unsigned)B), 32, 0, st>>>(y.p, x.p, alpha_log, beta_log, x.C, x.chunks, x.T, x.Tp, x.pad);
+    act1d_c8t_edge_kernel<<<dim3((unsigned)x.chunks, (unsigned)B), 32, 0, st>>>(y.p, x.p, alpha_log, beta_log, x.C, x.chunks, x.T, x.Tp, x.pad, x.lens, x.len_mul);
     BVG_LAUNCHED();
   }
   return BVG_OK;

@@ -66,6 +66,7 @@ struct ActConvTcParams {
   const __nv_bfloat16* edge;          // [B][2 sides][3 rows][rc][8]: exact a(x)[0..2], a(x)[T-3..T-1]
   int C, rc, S, Cin_p, NB, Cout, K, dil, lo, LH, SR, NP;
   int T, RL, NG, nitems;
+  const int* lens; int len_mul;       // ragged batch: utterance b has lens[b] * len_mul rows (else T)
   int nxs, nas, nacc, w_resident, w_slots;
   int nu, ny; uint32_t colA, colY, colC;
   int pace;                           // conv MMAs per pacing group (two groups in flight at most)
@@ -88,13 +89,17 @@ struct ActConvTcParams {
 #define TCF_TRACE(ev, idx) do { } while (0)
 #endif
 
-struct TcItem { int b, grp, nblk; };
+struct TcItem { int b, grp, nblk, T; };
+// WARP: called by a fully converged warp (rows_of shuffles, which also marks the length warp-uniform for ptxas); false for the
+// single-lane weight producer
+template <bool WARP = true>
 __device__ __forceinline__ TcItem tc_item(const ActConvTcParams& P, int item) {
   TcItem it;
   it.b = item / P.NG;
   it.grp = item - it.b * P.NG;
   const int r0 = it.grp * P.S * P.RL;
-  it.nblk = 4 * ((min(P.T, r0 + P.RL) - r0 + 127) >> 7);
+  it.T = WARP ? rows_of(P.lens, P.len_mul, it.b, P.T) : (P.lens ? __ldg(P.lens + it.b) * P.len_mul : P.T);
+  it.nblk = 4 * max(0, (min(it.T, r0 + P.RL) - r0 + 127) >> 7);       // 0: the whole item lies past the utterance's end
   return it;
 }
 __device__ __forceinline__ int seg_r0(const ActConvTcParams& P, const TcItem& it, int s) { return (it.grp * P.S + s) * P.RL; }
@@ -105,9 +110,9 @@ __device__ __forceinline__ bool x_edge(const ActConvTcParams& P, const TcItem& i
   bool e = false;
   for (int s = 0; s < P.S; ++s) {
     const int r0 = seg_r0(P, it, s);
-    if (r0 >= P.T) break;
+    if (r0 >= it.T) break;
     const int ts = xstage_t0(r0, st);
-    e = e || ts < 0 || ts + kXR > P.T;
+    e = e || ts < 0 || ts + kXR > it.T;
   }
   return e;
 }
@@ -116,9 +121,9 @@ __device__ __forceinline__ bool tile_edge(const ActConvTcParams& P, const TcItem
   bool e = false;
   for (int s = 0; s < P.S; ++s) {
     const int r0 = seg_r0(P, it, s);
-    if (r0 >= P.T) break;
+    if (r0 >= it.T) break;
     const int m0 = r0 + 128 * n;
-    e = e || m0 == 0 || m0 + 128 + P.LH > P.T - 3;
+    e = e || m0 == 0 || m0 + 128 + P.LH > it.T - 3;
   }
   return e;
 }
@@ -207,7 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiConst& E, int seg_t0, int
   const float* bp = bias_s + E.sl0 * 16;
   auto offset = [&](int r0_, int sl_) -> uint32_t {                 // element offset of (row, chunk 2 sl), ~0 if not an output row
     const int t = r0_ + t_in_seg;
-    return (r0_ < E.T && t < E.T && !TCF_DRY(16)) ? (uint32_t)(E.row_base + t) * 8u + (uint32_t)sl_ * E.cs2 : ~0u;
+    return (r0_ < E.T && t < E.T) ? (uint32_t)(E.row_base + t) * 8u + (uint32_t)sl_ * E.cs2 : ~0u;
   };
   uint4 c1[2], c2[2], n1[2], n2[2];
   auto load_res = [&](uint32_t off, uint4 (&e1)[2], uint4 (&e2)[2]) {
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       const int ps = lane / P.rc, pcc = lane - ps * P.rc;               // lane L < 12 issues the copy of chunk-slot L
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
         const int nstages = (it.nblk + 4 + kXB - 1) / kXB;
         const __nv_bfloat16* xb = P.x + (int64_t)it.b * P.x_bstride;
         for (int st = 0; st < nstages; ++st) {
@@ -364,9 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             uint32_t total = 0;
             for (int s = 0; s < P.S; ++s) {
               const int r0 = seg_r0(P, it, s);
-              if (r0 >= P.T) break;
+              if (r0 >= it.T) break;
               const int ts = xstage_t0(r0, st);
-              const int lo = max(ts, 0), hi = min(ts + kXR, P.T);
+              const int lo = max(ts, 0), hi = min(ts + kXR, it.T);
               if (hi > lo) total += (uint32_t)(hi - lo) * 16u * (uint32_t)P.rc;
             }
             mbar_expect_tx(full, total);
@@ -375,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           if (lane < kSlots) {
             const int r0 = seg_r0(P, it, ps);
             const int ts = xstage_t0(r0, st);
-            const int lo = max(ts, 0), hi = min(ts + kXR, P.T);
-            if (r0 < P.T && hi > lo) {
+            const int lo = max(ts, 0), hi = min(ts + kXR, it.T);
+            if (r0 < it.T && hi > lo) {
               bulk_g2s(smem_u32(xsm + xr.s * kXStageBytes) + (uint32_t)((lane * kXR + (lo - ts)) * 16),
                        xb + ((int64_t)pcc * P.x_tp + P.x_pad + lo) * 8, (uint32_t)(hi - lo) * 16u, full);
             }
@@ -396,7 +402,8 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         Ring wr;
         const int ncb = (P.Cin_p + 63) >> 6;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-          const TcItem it = tc_item(P, item);
+          const TcItem it = tc_item<false>(P, item);
+        if (it.nblk <= 0) continue;
           for (int n = 0; n < (it.nblk >> 2); ++n)
             for (int cb = 0; cb < ncb; ++cb) {
               const int kcn = min(8, (P.Cin_p >> 3) - cb * 8);
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       TcItem xit = xv ? tc_item(P, xi) : TcItem{0, 0, 0}, tit = xit;
       auto x_skip = [&]() {              // advance to the next input tile that needs patching
         while (xv) {
-          const int nstages = (xit.nblk + 4 + kXB - 1) / kXB;
+          const int nstages = xit.nblk > 0 ? (xit.nblk + 4 + kXB - 1) / kXB : 0;      // (empty items are skipped by every role)
           if (xst >= nstages) { xi += gridDim.x; xst = 0; xv = xi < P.nitems; if (xv) xit = tc_item(P, xi); continue; }
           if (x_edge(P, xit, xst)) return;
           ++xst; xr.next(P.nxs);
@@ -439,10 +446,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           uint4* stage = reinterpret_cast<uint4*>(xsm + xr.s * kXStageBytes);
           for (int s = 0; s < P.S; ++s) {
             const int r0 = seg_r0(P, xit, s);
-            if (r0 >= P.T) break;
+            if (r0 >= xit.T) break;
             const int ts = xstage_t0(r0, xst);
             const int nlo = min(max(-ts, 0), kXR);                       // rows [0, nlo): t < 0
-            const int rhi = min(max(P.T - ts, 0), kXR);                  // rows [rhi, kXR): t >= T
+            const int rhi = min(max(xit.T - ts, 0), kXR);                // rows [rhi, kXR): t >= T
             if (nlo == 0 && rhi == kXR) continue;
             for (int cc = 0; cc < P.rc; ++cc) {
               uint4* base = stage + (s * P.rc + cc) * kXR;
@@ -469,10 +476,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           const uint4 z = make_uint4(0, 0, 0, 0);
           for (int s = 0; s < P.S; ++s) {
             const int r0 = seg_r0(P, tit, s);
-            if (r0 >= P.T) break;
+            if (r0 >= tit.T) break;
             const int tA = r0 + 128 * tn - P.LH;                         // time of stage row 0
             const int zlo = min(max(-tA, 0), P.SR);                      // rows [0, zlo): t < 0
-            const int zhi = min(max(P.T - tA, 0), P.SR);                 // rows [zhi, SR): t >= T
+            const int zhi = min(max(tit.T - tA, 0), P.SR);               // rows [zhi, SR): t >= T
             for (int cc = 0; cc < P.rc; ++cc) {
               uint4* base = stage + (s * P.rc + cc) * P.SR;
               for (int r = lane; r < zlo; r += 32) base[r] = z;
@@ -481,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             // exact a(x)[0..2] and a(x)[T-3..T-1]: lane -> (side, row, chunk)
             for (int e = lane; e < 6 * P.rc; e += 32) {
               const int sr = e / P.rc, cc = e - sr * P.rc;               // sr = side * 3 + row
-              const int t = sr < 3 ? sr : P.T - 6 + sr;
+              const int t = sr < 3 ? sr : tit.T - 6 + sr;
               const int r = t - tA;
               if (r >= 0 && r < P.SR) stage[(s * P.rc + cc) * P.SR + r] = eb[sr * P.rc + cc];
             }
@@ -509,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
         const int nup = it.nblk + 4;
         for (int nu = 0; nu < nup; ++nu) {
           const int pos = nu % kXB;
@@ -548,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       long long dbg_wa = 0, dbg_wy = 0;
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
         int next_a = -2;
         for (int j = -1; j <= it.nblk; ++j) {
           while (next_a <= j + 1) {
@@ -615,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       };
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
         for (int n = 0; n < (it.nblk >> 2); ++n) {
           {
             DBG_T0();
@@ -683,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     };
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
       const int iend = it.nblk + 1;
       for (int i = -2; i <= iend; ++i, ++nb, ur.next(nu)) {
         const int sl = i & 3;
@@ -752,6 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     };
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
       const int nblk = it.nblk;
       for (int j = -1; j <= nblk; ++j) {
         const int p = j & 3;
@@ -807,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       const int f0 = set ? nslt >> 1 : 0, f1 = set ? nslt : nslt >> 1;
       E.nsl = P.NB >> 4;
       E.sg0 = f0 / E.nsl; E.sl0 = f0 - E.sg0 * E.nsl; E.cnt = f1 - f0;
-      E.T = P.T; E.RL = P.RL; E.row_base = P.y_pad;
+      E.T = P.T; E.RL = P.RL; E.row_base = P.y_pad;                  // (E.T is set per item: ragged batches)
       E.cs = (uint32_t)P.y_tp * 8u; E.cs2 = 2u * E.cs;
       E.scale = P.scale; E.do_scale = P.scale != 1.f;
     }
@@ -817,17 +829,20 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     const bool has_r1 = P.res1 != nullptr, has_r2 = P.res2 != nullptr;
     // the tile that holds row T - 1: global segment (T - 1) / RL -> item group, tile within the segment
     const bool zero_pads = P.zero_pads != 0;
-    const int zl_gs = (P.T - 1) / P.RL, zl_grp = zl_gs / S, zl_n = ((P.T - 1) - zl_gs * P.RL) >> 7;
+    const int RLc = P.RL;
     Ring cr;
     uint32_t tile = 0;
     long long dbg_ew = 0, dbg_eb = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
+        if (it.nblk <= 0) continue;
       __nv_bfloat16* yb = P.y + (int64_t)it.b * P.y_bstride;
       const __nv_bfloat16* r1 = has_r1 ? P.res1 + (int64_t)it.b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = has_r2 ? P.res2 + (int64_t)it.b * P.y_bstride : nullptr;
       const int seg_t0 = seg_r0(P, it, E.sg0);
       const int ntile = it.nblk >> 2;
+      E.T = it.T;
+      const int zl_gs = (it.T - 1) / RLc, zl_grp = zl_gs / S, zl_n = ((it.T - 1) - zl_gs * RLc) >> 7;
       for (int n = 0; n < ntile; ++n, ++tile) {
         {
           // one warp polls the mbarrier, the other seven park on a named barrier (no issue slots: the SM is issue-bound)
@@ -871,7 +886,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
                 *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + (i % P.y_pad)) * 8) = z;
             if (it.grp == zl_grp && n == zl_n)
               for (int i = et; i < npad; i += nth)
-                *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + P.y_pad + P.T + (i % P.y_pad)) * 8) = z;
+                *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_pad) * P.y_tp + P.y_pad + it.T + (i % P.y_pad)) * 8) = z;
           }
           DBG_ADD(dbg_eb);
         }
@@ -892,9 +907,11 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
 // stencil of act1d_core.cuh): edge[b][side][row][chunk][8] bf16.  One warp per (chunk, utterance).
 __global__ void __launch_bounds__(32) actconv_edge_kernel(__nv_bfloat16* __restrict__ edge, const __nv_bfloat16* __restrict__ x,
                                                           const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
-                                                          int C, int rc, int64_t x_bstride, int T, int Tp, int pad) {
+                                                          int C, int rc, int64_t x_bstride, int T, int Tp, int pad,
+                                                          const int* __restrict__ lens, int len_mul) {
   const int chunk = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
   if (lane >= 16) return;
+  if (lens) T = lens[b] * len_mul;
   constexpr int V = 8;
   const int side = lane >> 3, c8 = lane & 7;
   const int ch = chunk * 8 + c8;
@@ -963,6 +980,7 @@ int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, 
   P.alpha = act_alpha; P.beta = act_beta;
   P.edge = static_cast<const __nv_bfloat16*>(scratch);
   P.T = x.T; P.zero_pads = ep.zero_pads;
+  P.lens = x.lens; P.len_mul = x.len_mul;
   P.dbg = g_dbg_buf;
 #ifdef BVG_DEBUG
   if (const char* e = getenv("BVG_TCF_DRY")) P.dry = atoi(e);
@@ -1012,7 +1030,7 @@ int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, 
   BVG_TRY(smem_opt_in(actconv_tc_kernel, opted, 227 * 1024));
   ProfScope prof(st, KC_ACTCONV);
   actconv_edge_kernel<<<dim3((unsigned)P.rc, (unsigned)B), 32, 0, st>>>(static_cast<__nv_bfloat16*>(scratch), x.p, act_alpha, act_beta,
-                                                                       L.Cin, P.rc, P.x_bstride, x.T, x.Tp, x.pad);
+                                                                       L.Cin, P.rc, P.x_bstride, x.T, x.Tp, x.pad, x.lens, x.len_mul);
   BVG_LAUNCHED();
   actconv_tc_kernel<<<(unsigned)std::min<int64_t>(items, num_sms), kThreads, smem, st>>>(P);
   BVG_LAUNCHED();

@@ -80,6 +80,14 @@ int current_device_sms(int* sms);
 int env_int_once(const char* name, int dflt);
 #define BVG_ENV_ONCE(name, dflt) ([]() -> int { static const int v__ = bvg::env_int_once(name, dflt); return v__; }())
 
+// rows of utterance b in a (possibly ragged) batch; the shuffle marks the loaded value warp-uniform for ptxas (the
+// tcgen05.mma issue loops must stay on the uniform datapath: profiles/README.md, round 2)
+#ifdef __CUDACC__
+__device__ __forceinline__ int rows_of(const int* lens, int len_mul, int b, int T) {
+  return lens ? __shfl_sync(0xffffffffu, __ldg(lens + b) * len_mul, 0) : T;
+}
+#endif
+
 static inline size_t dtype_size(int dt) { return (dt == BVG_F32 || dt == BVG_F32X3) ? 4 : 2; }
 
 // ---- element load/store as float -----------------------------------------------------------

@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       int xs = 0, ws = 0;
       uint32_t xph = 0, wph = 0;
       long long dbg_prod_wait = 0;
+      bool w_loaded = false;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nb = tile % P.n_nblk;
         const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
         const int b = tile / (P.n_nblk * P.tiles_per_batch);
         const int q0 = mt * P.MT * 128;
+        if (P.lens && q0 * P.u - P.p >= __ldg(P.lens + b) * P.len_mul) continue;    // ragged batch: tile past the utterance's end
         const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
         const int64_t row_start = (int64_t)P.x_row0 + q0 - P.lo;    // first staged row within a chunk
         for (int cb = 0; cb < P.n_ci_blk; ++cb) {
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           const __nv_bfloat16* wsrc = P.w + ((int64_t)nb * P.Cin_p + (int64_t)cb * 64) * P.NB * P.ntaps;
           if (P.w_resident) {
             // the whole layer's weights stay in shared memory: fetched once, on this CTA's first tile
-            if (tile == (int)blockIdx.x)
+            if (!w_loaded)
               for (int tp = 0; tp < P.ntaps; ++tp) {
                 const int slot = cb * P.ntaps + tp;
                 mbar_expect_tx(&full_w[slot], wbytes);
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             }
           }
         }
+        w_loaded = true;                                            // (first PROCESSED tile: ragged batches skip tiles)
       }
       if (P.dbg) P.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait;
     }
@@ -163,7 +166,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       uint32_t xph = 0, wph = 0, aph = 0;
       long long dbg_wx = 0, dbg_ww = 0, dbg_wt = 0, dbg_issue = 0;   // (dbg_issue spans a whole channel block, weight waits included)
       const long long dbg_start = P.dbg ? clock64() : 0;
+      bool w_waited = false;
       for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
+        if (P.lens) {                                               // ragged batch: skip tiles past the utterance's end (as the other roles do)
+          const int mt_ = (tile / P.n_nblk) % P.tiles_per_batch, b_ = tile / (P.n_nblk * P.tiles_per_batch);
+          if (mt_ * P.MT * 128 * P.u - P.p >= rows_of(P.lens, P.len_mul, b_, P.Tout)) continue;
+        }
         if (!dry) { DBG_T0(); mbar_wait_backoff(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }   // epilogue drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dbase = tmem_base + (uint32_t)(as * acols);
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
           for (int tp = 0; tp < ntaps; ++tp) {
             const int slot = resident ? cb * ntaps + tp : ws;
-            if (!dry && (!resident || tile == first_tile)) {        // resident weights are waited for once
+            if (!dry && (!resident || !w_waited)) {                 // resident weights are waited for once
               const long long ww0 = P.dbg ? clock64() : 0;
               mbar_wait(&full_w[slot], resident ? 0u : wph);
               if (P.dbg) dbg_ww += clock64() - ww0;
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
           if (++xs == n_xst) { xs = 0; xph ^= 1; }
         }
         if (!dry) umma_commit_elect(&tmem_full[as]);
+        w_waited = true;
         if (++as == n_ast) { as = 0; aph ^= 1; }
       }
       if (dry) {                         // drain: wait for every issued MMA so the total is inclusive
@@ -241,6 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
       const int mt = (tile / P.n_nblk) % P.tiles_per_batch;
       const int b = tile / (P.n_nblk * P.tiles_per_batch);
       const int q0 = mt * P.MT * 128;
+      const int Tout_b = rows_of(P.lens, P.len_mul, b, P.Tout);
+      if (q0 * P.u - P.p >= Tout_b) continue;                           // ragged batch: tile past the utterance's end
       __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
       const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
         const int ms = a / P.NPH, s = a - ms * P.NPH;
         const int64_t q = (int64_t)q0 + ms * 128 + r;
         const int64_t t = q * P.u + s - P.p;
-        const bool valid = (t >= 0) && (t < P.Tout);
+        const bool valid = (t >= 0) && (t < Tout_b);
         const int64_t rowoff = ((int64_t)P.y_row0 + (valid ? t : 0)) * 8;
         for (int grp = (half - a * ngrp) & 1; grp < ngrp; grp += 2) {
           // columns [c0, c0+32) of accumulator a (the last group may be 16 wide)
@@ -385,9 +396,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
         if (mt == 0)
           for (int i = et; i < chn * P.y_row0; i += kEpiWarps * 32)
             *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
-        if (mt == P.tiles_per_batch - 1)
+        if (mt == (Tout_b - 1) / (P.MT * 128))                          // (zero_pads is only used by plain convs: u = 1)
           for (int i = et; i < chn * P.y_row0; i += kEpiWarps * 32)
-            *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
+            *reinterpret_cast<uint4*>(yb + ((int64_t)(ch0 + i / P.y_row0) * P.y_tp + P.y_row0 + Tout_b + (i % P.y_row0)) * 8) = z;
       }
     }
     if (P.dbg && threadIdx.x == kEpiWarp0 * 32) { P.dbg[blockIdx.x * 8 + 6] = dbg_ewait; P.dbg[blockIdx.x * 8 + 7] = dbg_ebusy; }
@@ -442,11 +453,12 @@ __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* _
 // plain [B,C,T] (fp32 or bf16) <-> c8t bf16
 template <typename TS>
 __global__ void to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const TS* __restrict__ src, int64_t sb, int64_t sc,
-                              int64_t st_, int C, int chunks, int T, int Tp, int pad) {
+                              int64_t st_, int C, int chunks, int T, int Tp, int pad, const int* __restrict__ lens, int len_mul) {
   // one thread per (b, chunk, row) 16-byte vector, pads and padding channels zeroed
   const int64_t n = (int64_t)gridDim.y * chunks * Tp;
   (void)n;
   const int b = blockIdx.y;
+  if (lens) T = lens[b] * len_mul;                                  // ragged batch: rows past the utterance's end are zero
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)chunks * Tp; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i / Tp), row = (int)(i % Tp);
     const int t = row - pad;
@@ -619,6 +631,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   P.Cout = L.Cout;
   P.x = x.p; P.x_bstride = (int64_t)x.chunks * x.Tp * 8; P.x_tp = x.Tp; P.x_row0 = x.pad;
   P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad; P.y_chunks = y.chunks;
+  P.lens = y.lens; P.len_mul = y.len_mul;
+  BVG_CHECK_ARG(!y.lens || !ep.yf32, "conv_umma: ragged batches are a bf16 c8t feature");
   P.w = L.w;
   P.bias = ep.bias; P.cond = ep.cond; P.cond_B = (int)ep.cond_B; P.scale = ep.scale;
   P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
@@ -674,11 +688,11 @@ int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64
   dim3 grid((unsigned)std::min<int64_t>(((int64_t)dst.chunks * dst.Tp + 255) / 256, 4096), (unsigned)B);
   ProfScope prof(st, KC_OTHER);
   if (src_dtype == BVG_F32)
-    to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+    to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
   else if (src_dtype == BVG_BF16)
-    to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+    to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
   else if (src_dtype == BVG_F16)
-    to_c8t_kernel<__half><<<grid, 256, 0, st>>>(dst.p, (const __half*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad);
+    to_c8t_kernel<__half><<<grid, 256, 0, st>>>(dst.p, (const __half*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
   else { set_error("to_c8t: unsupported dtype"); return BVG_ERR_INVALID; }
   BVG_LAUNCHED();
   return BVG_OK;

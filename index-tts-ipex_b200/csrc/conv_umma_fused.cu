@@ -65,7 +65,7 @@ __host__ __device__ inline size_t fused_fixed_smem(int NB, int Cin_p) {
 template <int NCH, bool HAS_R2>
 __device__ __forceinline__ void fused_epilogue_tile(const UmmaConvParams& P, __nv_bfloat16* yb, const __nv_bfloat16* r1,
                                                     const __nv_bfloat16* r2, const float* bias_s, uint32_t tbase, int q0, int r,
-                                                    int nacc, uint64_t* tmem_full_bar, uint32_t aph, long long& dbg_ewait) {
+                                                    int nacc, uint64_t* tmem_full_bar, uint32_t aph, long long& dbg_ewait, int Tout_b) {
   constexpr int W = 8 * NCH;                                        // columns per slice
   const int nsl = (P.NB + W - 1) / W;                               // slices per accumulator (the last may be narrower)
   const int cs = P.y_tp * 8;                                        // elements between channel chunks
@@ -74,7 +74,7 @@ __device__ __forceinline__ void fused_epilogue_tile(const UmmaConvParams& P, __n
   // element offset (within the batch element) of accumulator row `a`, chunk 0; -1 if the row is not an output
   auto row_off = [&](int a) -> int {
     const int row = a * 128 + r;
-    return (a < nacc && row < P.rows_out && q0 + row < P.Tout) ? (P.y_row0 + q0 + row) * 8 : -1;
+    return (a < nacc && row < P.rows_out && q0 + row < Tout_b) ? (P.y_row0 + q0 + row) * 8 : -1;
   };
   auto load_res = [&](const __nv_bfloat16* rp, int a, int si, uint4 (&e)[NCH]) {
     const int ro = rp ? row_off(a) : -1;
@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
           const int mt = tile % P.tiles_per_batch;
           const int b = tile / P.tiles_per_batch;
           const int q0 = mt * P.rows_out;
+          if (P.lens && q0 >= __ldg(P.lens + b) * P.len_mul) continue;          // ragged batch: tile past the utterance's end
           const __nv_bfloat16* xb = P.x + (int64_t)b * P.x_bstride;
           // raw tile row i <-> padded-space row r0 + i, r0 = x_row0 + q0 - lo - 8; clipped to the chunk [0, x_tp)
           // (rows outside only ever feed replicate-padded positions, which the stencil overrides)
@@ -233,8 +234,11 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       if (lane == 0) {
         int ws = 0;
         uint32_t wph = 0;
+        bool w_loaded = false;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          if (P.w_resident && tile != (int)blockIdx.x) break;          // resident weights are fetched once
+          if (P.lens && (tile % P.tiles_per_batch) * P.rows_out >= __ldg(P.lens + tile / P.tiles_per_batch) * P.len_mul) continue;
+          if (P.w_resident && w_loaded) break;                         // resident weights are fetched once
+          w_loaded = true;
           for (int blk = 0; blk < nblk; ++blk) {
             const int g0 = blk * (kFBlk / 8);                            // first global chunk of the block
             const int nc = min(kFBlk / 8, (P.Cin_p >> 3) - g0);          // chunks the MMAs of this block read
@@ -273,7 +277,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         const long long dbg_start = P.dbg ? clock64() : 0;
         unsigned long long dbg_ns0 = 0;
         if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
+        bool w_waited = false;
         for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
+          if (P.lens && (tile % P.tiles_per_batch) * P.rows_out >= rows_of(P.lens, P.len_mul, tile / P.tiles_per_batch, P.Tout)) continue;
           { DBG_T0(); mbar_wait_backoff(&tmem_empty[as], aph ^ 1); DBG_ADD(dbg_wt); }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t dbase = tmem_base + (uint32_t)(as * acc_cols);
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             const uint32_t a_cb = x_base + (uint32_t)xs * xsb16;
             for (int tp = 0; tp < P.ntaps; ++tp) {
               const int slot = P.w_resident ? blk * P.ntaps + tp : ws;
-              if (!P.w_resident || tile == first_tile) {
+              if (!P.w_resident || !w_waited) {
                 DBG_T0();
                 mbar_wait(&full_w[slot], P.w_resident ? 0u : wph);
                 DBG_ADD(dbg_ww);
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
             if (++xs == nast) { xs = 0; xph ^= 1; }
           }
           umma_commit_elect(&tmem_full[as]);
+          w_waited = true;
           if (++as == P.acc_stages) { as = 0; aph ^= 1; }
         }
         if (P.dbg && lane == 0 && ii == 0) { long long* d = P.dbg + blockIdx.x * 16; d[3] = dbg_wx; d[4] = dbg_wt; d[5] = clock64() - dbg_start; d[8] = dbg_ww;
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       const int64_t boff = (int64_t)(t / P.tiles_per_batch) * P.y_bstride;
       for (int a = 0; a < nacc; ++a) {
         const int row = a * 128 + r;
-        if (row < P.rows_out && nq0 + row < P.Tout) {
+        if (row < P.rows_out && nq0 + row < P.Tout) {                  // (ragged batches: a few prefetches past the end, harmless)
           const int64_t ro = boff + (P.y_row0 + nq0 + row) * 8;
           for (int co = 0; co < cout8; co += 8) {
             if (P.res1) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.res1 + ro + (co >> 3) * cs));
@@ -349,6 +356,8 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       const int mt = tile % P.tiles_per_batch;
       const int b = tile / P.tiles_per_batch;
       const int q0 = mt * P.rows_out;
+      const int Tout_b = rows_of(P.lens, P.len_mul, b, P.Tout);
+      if (q0 >= Tout_b) continue;                                     // ragged batch: tile past the utterance's end
       __nv_bfloat16* yb = P.y + (int64_t)b * P.y_bstride;
       const __nv_bfloat16* r1 = P.res1 ? P.res1 + (int64_t)b * P.y_bstride : nullptr;
       const __nv_bfloat16* r2 = P.res2 ? P.res2 + (int64_t)b * P.y_bstride : nullptr;
@@ -358,8 +367,8 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
       DBG_T0();
       const long long ew0 = dbg_ewait;
       const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_cols);
-      if (r2) fused_epilogue_tile<2, true>(P, yb, r1, r2, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait);
-      else fused_epilogue_tile<4, false>(P, yb, r1, nullptr, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait);
+      if (r2) fused_epilogue_tile<2, true>(P, yb, r1, r2, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait, Tout_b);
+      else fused_epilogue_tile<4, false>(P, yb, r1, nullptr, bias_s, tbase, q0, r, nacc, &tmem_full[as], aph, dbg_ewait, Tout_b);
       // all of this warp's TMEM reads for the stage are complete: hand it back to the MMA issuers
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -373,9 +382,9 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
         if (mt == 0)
           for (int i = et; i < chn * P.y_row0; i += 128)
             *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + (i % P.y_row0)) * 8) = z;
-        if (mt == P.tiles_per_batch - 1)
+        if (mt == (Tout_b - 1) / P.rows_out)
           for (int i = et; i < chn * P.y_row0; i += 128)
-            *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + P.y_row0 + P.Tout + (i % P.y_row0)) * 8) = z;
+            *reinterpret_cast<uint4*>(yb + ((int64_t)(i / P.y_row0) * P.y_tp + P.y_row0 + Tout_b + (i % P.y_row0)) * 8) = z;
       }
       DBG_ADD(dbg_ebusy);
       dbg_ebusy -= dbg_ewait - ew0;
@@ -393,6 +402,8 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mt = tile % P.tiles_per_batch;
       const int q0 = mt * P.rows_out;
+      const int Tout_b = P.lens ? __ldg(P.lens + tile / P.tiles_per_batch) * P.len_mul : P.Tout;
+      if (q0 >= Tout_b) continue;                                   // ragged batch: tile past the utterance's end
       const int64_t t_first = (int64_t)q0 - P.lo;                   // time index of A-tile row 0
       for (int blk = 0; blk < nblk; ++blk) {
         const int nwords = min(kFBlk / 2, (P.Cin - blk * kFBlk + 1) >> 1);   // real channel-pair words per row in this block
@@ -412,12 +423,12 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
           const uint32_t* inw = raw + (size_t)(cg * XRAW + j0) * 4 + pp;      // window row i <-> raw row j0 + i
           uint32_t* outw = xo + (size_t)(cg * XA + j0) * 4 + pp;
           const float4 sp = snk[chA >> 1];
-          const bool interior = (t0 - 5 >= 0) && (t0 + V + 4 <= (int64_t)P.Tout - 1) && (chA + 1 < P.Cin);
+          const bool interior = (t0 - 5 >= 0) && (t0 + V + 4 <= (int64_t)Tout_b - 1) && (chA + 1 < P.Cin);
           if (interior) {
             act1d_window2<V>([&](int j) { return unpack_bf16x2(inw[j * 4]); },
                              [&](int q, float ya, float yb) { outw[q * 4] = pack2(ya, yb); },
                              pk2(sp.x, sp.z), pk2(sp.y, sp.w));
-          } else if ((t0 + V - 1 >= 0) && (t0 < P.Tout)) {
+          } else if ((t0 + V - 1 >= 0) && (t0 < Tout_b)) {
             uint32_t wd[V + 16];
 #pragma unroll
             for (int j = 0; j < V + 16; ++j) wd[j] = inw[j * 4];
@@ -430,10 +441,10 @@ __global__ void __launch_bounds__(kFThreads, 1) conv_umma_fused_kernel(const Umm
 #pragma unroll
                 for (int j = 0; j < V + 16; ++j)
                   xw[j] = h ? __uint_as_float(wd[j] & 0xffff0000u) : __uint_as_float(wd[j] << 16);
-                act1d_window<V, false>(xw, yv, h ? sp.z : sp.x, h ? sp.w : sp.y, t0, (int64_t)P.Tout);
+                act1d_window<V, false>(xw, yv, h ? sp.z : sp.x, h ? sp.w : sp.y, t0, (int64_t)Tout_b);
 #pragma unroll
                 for (int q = 0; q < V; ++q)
-                  if (t0 + q < 0 || t0 + q >= P.Tout) yv[q] = 0.f;       // the conv's zero padding
+                  if (t0 + q < 0 || t0 + q >= Tout_b) yv[q] = 0.f;       // the conv's zero padding
               } else {
 #pragma unroll
                 for (int q = 0; q < V; ++q) yv[q] = 0.f;
@@ -508,6 +519,7 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
   P.w = L.w;
   P.bias = ep.bias; P.scale = ep.scale; P.res1 = ep.res1; P.res2 = ep.res2; P.zero_pads = ep.zero_pads;
   P.act_alpha = act_alpha; P.act_beta = act_beta;
+  P.lens = y.lens; P.len_mul = y.len_mul;
   P.dbg = ep.dbg;
 #ifdef BVG_DEBUG
   P.dry = BVG_ENV_ONCE("BVG_FUSE_DRY", 0);     // debug builds only: skip the stencil math (timing experiments, results are garbage)

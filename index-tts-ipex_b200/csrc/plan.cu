@@ -498,8 +498,15 @@ UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1
 
 // The bf16 throughput path: c8t activations, tcgen05 convs (models.py:220-248).
 int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, const GenWs& g, int64_t B, int64_t T0, int64_t Bm,
-                     float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st) {
+                     float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st, const int* lens = nullptr) {
   const bvg_config& c = P->cfg;
+  // ragged batches (bvg_decode_varlen): `lens` = device int32 [B] latent-frame counts; every tensor of a stage carries them
+  // with the stage's cumulative upsampling factor, the kernels clip at each utterance's own length (umma.cuh, C8T::lens)
+  auto make_c8t = [&](void* p, int C, int T) {
+    C8T t = bvg::make_c8t(p, C, T);
+    t.lens = lens; t.len_mul = (int)(T / T0);
+    return t;
+  };
   // latent [B,T0,gpt_dim] fp32 (channels-last) -> c8t bf16
   C8T lat = make_c8t(g.T1, c.gpt_dim, (int)T0);
   // (the GPT hands its latent over in its autocast dtype, gpt/model.py:462-477 under infer.py:194: fp16 / bf16 / fp32 are
@@ -929,9 +936,29 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
                         workspace_bytes, stream);
 }
 
+static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtype, const int* lens, const float* mel,
+                      const float* spk_in, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16,
+                      int64_t t_lo_pad, int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream);
+
 int bvg_decode_lat(const bvg_plan* P, const void* latent_any, int latent_dtype, const float* mel, const float* spk_in, int64_t B,
                    int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16, int64_t t_lo_pad,
                    int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_any(P, latent_any, latent_dtype, nullptr, mel, spk_in, B, T0, Bm, Tm, dtype, wav, pcm16, t_lo_pad, t_hi_pad,
+                    workspace, workspace_bytes, stream);
+}
+
+int bvg_decode_varlen(const bvg_plan* P, const void* latent, int latent_dtype, const int32_t* lens_dev, const float* mel,
+                      const float* spk, int64_t B, int64_t T0_max, int64_t Bm, int64_t Tm, float* wav, int16_t* pcm16,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  BVG_CHECK_ARG(lens_dev, "decode_varlen: null length array");
+  BVG_CHECK_ARG(P && P->umma, "decode_varlen: ragged batches run on the bf16 tensor-core path (plan finalised without its packs)");
+  return decode_any(P, latent, latent_dtype, lens_dev, mel, spk, B, T0_max, Bm, Tm, BVG_BF16, wav, pcm16, 0, 0, workspace,
+                    workspace_bytes, stream);
+}
+
+static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtype, const int* lens, const float* mel,
+                      const float* spk_in, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16,
+                      int64_t t_lo_pad, int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BVG_CHECK_ARG(latent_dtype == BVG_F32 || latent_dtype == BVG_BF16 || latent_dtype == BVG_F16,
                 "decode: latent dtype must be BVG_F32, BVG_BF16 or BVG_F16");
@@ -969,7 +996,8 @@ int bvg_decode_lat(const bvg_plan* P, const void* latent_any, int latent_dtype, 
         BVG_TRY(conv_f32(g.cond[i + 1], P->C[i + 1], spk, nullptr, E, 1, 1, P->conds[i], ep, Bm, 1, 1, 0, st));
   }
   if (dtype == BVG_BF16 && P->umma)
-    return decode_bf16_umma(P, latent_any, latent_dtype, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st);
+    return decode_bf16_umma(P, latent_any, latent_dtype, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st, lens);
+  BVG_CHECK_ARG(!lens, "decode_varlen: ragged batches need the bf16 path");
   if (latent_dtype != BVG_F32) {
     // the fp32 paths read the latent through the CUDA-core conv: widen it once into the staging buffer
     BVG_TRY(cast_to_f32_launch(g.latent_dev, latent_any, latent_dtype, B * T0 * c.gpt_dim, st));

@@ -11,6 +11,12 @@ constexpr int kC8tPad = 32;    // zero rows before t=0 and after t=T-1 (max conv
 struct C8T {
   __nv_bfloat16* p = nullptr;
   int C = 0, chunks = 0, T = 0, Tp = 0, pad = kC8tPad;
+  // ragged batches (bvg_decode_varlen): utterance b holds lens[b] * len_mul valid rows (device int32 array of latent-frame
+  // counts, times the stage's cumulative upsampling factor); T is then the LONGEST utterance = the memory geometry.  Every
+  // kernel clips its tiles, its edge semantics (zero / replicate padding) and its zero halo rows at the utterance's own
+  // length, so each utterance of a ragged batch is computed exactly as if decoded alone.  nullptr: all utterances have T rows.
+  const int* lens = nullptr;
+  int len_mul = 1;
   int64_t batch_stride() const { return (int64_t)chunks * Tp * 8; }
 };
 inline C8T make_c8t(void* p, int C, int T) {
@@ -73,6 +79,7 @@ struct UmmaConvParams {
   long long* dbg;
   int dry;
   int n_issuers;
+  const int* lens; int len_mul;       // ragged batch: valid OUTPUT rows of utterance b = lens[b] * len_mul (else Tout)
   int transposed, dil;
   int relu, act;
   int Cin;                            // true input channels (fused activation)

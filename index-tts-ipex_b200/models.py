@@ -501,14 +501,70 @@ class BigVGAN(nn.Module):
         return torch.cat(outs, dim=-1)
 
     @torch.no_grad()
+    @torch.no_grad()
+    def decode_varlen(self, latents, mel_ref=None, spk=None, pcm16=False, lens=None):
+        """True batched vocoding of utterances of different lengths in ONE call (bf16 path; `bvg_decode_varlen`).
+        `latents`: a sequence of `[T0_i, gpt_dim]` tensors, or a padded `[B, T0_max, gpt_dim]` tensor with `lens` (ints).
+        Exactly one of `mel_ref` `[B' in {1, B}, Tm, num_mels]` / `spk` `[B', 1, emb]`.  Returns `[B, 1, T0_max * up]` fp32
+        (or `[B, T0_max * up]` int16): utterance b's first `lens[b] * up` samples are what decoding it alone gives (bit for
+        bit when it is long enough to take the same kernels alone: >= 64 latent frames), the rest of its row is zero."""
+        if self.precision != "bf16":
+            raise RuntimeError("decode_varlen: ragged batches run on the bf16 tensor-core path (set precision='bf16')")
+        if (mel_ref is None) == (spk is None):
+            raise RuntimeError("pass exactly one of mel_ref / spk")
+        if torch.is_tensor(latents):
+            if lens is None:
+                raise RuntimeError("decode_varlen: a padded latent tensor needs `lens`")
+            x = latents.detach()
+            lens = [int(v) for v in lens]
+        else:
+            seq = [t.detach() if t.dim() == 2 else t.detach().squeeze(0) for t in latents]
+            lens = [int(t.shape[0]) for t in seq]
+            x = torch.nn.utils.rnn.pad_sequence(seq, batch_first=True)
+        if x.dim() != 3 or x.shape[-1] != int(self.h.gpt_dim) or len(lens) != x.shape[0]:
+            raise RuntimeError(f"decode_varlen: expected [B, T0_max, {int(self.h.gpt_dim)}] latents and B lengths")
+        B, T0 = int(x.shape[0]), int(x.shape[1])
+        if min(lens) < 1 or max(lens) > T0:
+            raise RuntimeError(f"decode_varlen: lengths must be in [1, {T0}]")
+        lat_code = {torch.float32: capi.BVG_F32, torch.bfloat16: capi.BVG_BF16, torch.float16: capi.BVG_F16}.get(x.dtype)
+        if lat_code is None:
+            x, lat_code = x.to(torch.float32), capi.BVG_F32
+        x = x.contiguous()
+        dev = x.device
+        plan = self._ensure_plan(dev)
+        lens_dev = torch.tensor(lens, dtype=torch.int32, device=dev)
+        if mel_ref is not None:
+            cond = mel_ref.detach().to(dev, torch.float32).contiguous()
+            Bm, Tm = cond.shape[0], cond.shape[1]
+            mel_ptr, spk_ptr = cond.data_ptr(), None
+        else:
+            cond = spk.detach().to(dev, torch.float32).reshape(spk.shape[0], -1).contiguous()
+            Bm, Tm = cond.shape[0], 1
+            mel_ptr, spk_ptr = None, cond.data_ptr()
+        Lout = T0 * self.total_upsample
+        nbytes = int(capi.lib().bvg_workspace_bytes(plan, B, T0, Tm, capi.BVG_BF16))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if pcm16:
+            out = torch.empty(B, Lout, device=dev, dtype=torch.int16)
+            wav_ptr, pcm_ptr = None, out.data_ptr()
+        else:
+            out = torch.empty(B, 1, Lout, device=dev, dtype=torch.float32)
+            wav_ptr, pcm_ptr = out.data_ptr(), None
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            capi.check(capi.lib().bvg_decode_varlen(plan, x.data_ptr(), lat_code, lens_dev.data_ptr(), mel_ptr, spk_ptr, B, T0, Bm,
+                                                    Tm, wav_ptr, pcm_ptr, ws.data_ptr(), ws.numel(), st), "bvg_decode_varlen")
+        return out
+
     def decode_ragged(self, latents, mel_refs, pcm16=False):
         """Batched vocoding of utterances of DIFFERENT lengths (what `infer_fast` works around by concatenating two
         sentences in time at B = 1, `indextts/infer.py:480-503`).  `latents` is a sequence of `[T0_i, gpt_dim]`
         tensors, `mel_refs` one `[Tm, num_mels]` reference for all of them or a sequence with one per utterance.
-        The generator has no length masks and its edge handling (zero-padded convs, replicate-padded anti-alias
-        filters) depends on where each utterance ends, so padding to a common length would change the last ~35
-        frames; instead utterances of equal length are batched together and every waveform equals the one a
-        single-utterance call returns.  Speaker embeddings are computed once per distinct reference.
+        The generator's edge handling (zero-padded convs, replicate-padded anti-alias filters) depends on where each
+        utterance ends, so plain padding to a common length would change the last ~35 frames.  On the bf16 path the kernels
+        take the per-utterance lengths and the whole ragged batch is ONE call (`decode_varlen`); on the fp32 paths
+        utterances of equal length are batched together.  Either way every waveform is the one a single-utterance call
+        returns.  Speaker embeddings are computed once per distinct reference.
         Returns a list of `[1, T0_i * 1024]` waveforms (or `[T0_i * 1024]` int16 with pcm16) in input order."""
         lat = [t if t.dim() == 2 else t.squeeze(0) for t in latents]
         n = len(lat)
@@ -527,6 +583,15 @@ class BigVGAN(nn.Module):
                 mm = m if m.dim() == 3 else m.unsqueeze(0)
                 spk_of[key] = self.speaker_embed(mm.to(dev))
         out = [None] * n
+        if self.precision == "bf16" and len({int(t.shape[0]) for t in lat}) > 1:
+            # bf16 path: ONE batched call, the kernels take the per-utterance lengths (bvg_decode_varlen)
+            spk = torch.cat([spk_of[(m.data_ptr(), tuple(m.shape))] for m in mels], 0)
+            y = self.decode_varlen(lat, spk=spk, pcm16=pcm16)
+            up = self.total_upsample
+            for i, t in enumerate(lat):
+                L = int(t.shape[0]) * up
+                out[i] = y[i, :L] if pcm16 else y[i, :, :L]
+            return out
         groups = {}
         for i, t in enumerate(lat):
             groups.setdefault(int(t.shape[0]), []).append(i)
