@@ -26,8 +26,8 @@
 //
 // Edges.  Rows t < 0 / t >= T of a staged tile are overwritten with x[0] / x[T-1] in shared memory (replicate padding of
 // the input, resample.py:28).  The replicate padding of the ACTIVATED signal (filter.py:90-92) only changes y[0..2] and
-// y[T-3..T-1]; those six rows per utterance, the zero halo rows and the padding channels are (re)written afterwards by
-// act1d_c8t_edge_kernel on the CUDA cores with the exact stencil of act1d_core.cuh.
+// y[T-3..T-1]; those six rows per utterance, the zero halo rows and the padding channels are written in the kernel's prologue
+// (act1d_edge_unit, CUDA cores, the exact stencil of act1d_core.cuh); the streaming part never stores them.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -76,7 +76,7 @@ struct ActTcParams {
   int64_t bstride;
   int cps, sps, nseg, ntile;      // chunks per tile, lane-chunk slots per segment, segments per item, channel tiles
   int RL, NG;                     // rows per range, range groups per utterance
-  int nitems;
+  int nitems, nb;
   const int* lens; int len_mul;   // ragged batch: utterance b has lens[b] * len_mul rows (else T)
   long long* dbg;                 // optional [grid][16] per-role cycle counters (bvg_debug_set_umma_counters)
   int dry;                        // BVG_DEBUG builds only: skip parts of the pipeline (bottleneck experiments, garbage results)
@@ -113,6 +113,41 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// The rows the tensor-core pass cannot get right plus the tensor's zero frame (see the header): y[0..2], y[T-3..T-1] with
+// the exact replicate-pad semantics, zero halo rows, zero padding channels, for one (chunk, utterance) by one warp.  The
+// streaming part of the kernel never stores those six rows, so this runs in its prologue (no ordering needed, no second
+// launch: 55 tiny launches per decode step were 12 % of the Activation1d time).
+__device__ __forceinline__ void act1d_edge_unit(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                                                const float* __restrict__ alpha_log, const float* __restrict__ beta_log, int C,
+                                                int chunks, int T, int Tp, int pad, int chunk, int b, int lane) {
+  const int64_t base = ((int64_t)b * chunks + chunk) * Tp;
+  if (lane < 16) {
+    constexpr int V = 8;
+    const int side = lane >> 3, c8 = lane & 7;
+    const int ch = chunk * 8 + c8;
+    const int64_t tg = side ? T - V : 0;
+    float xw[V + 16], yv[V];
+#pragma unroll
+    for (int i = 0; i < V + 16; ++i) {
+      const int64_t t = tg - 8 + i;
+      xw[i] = (t >= 0 && t < T) ? __bfloat162float(x[(base + pad + t) * 8 + c8]) : 0.f;
+    }
+    float sc0 = 0.f, sc1 = 0.f;
+    if (ch < C) snake_params<false>(alpha_log[ch], beta_log[ch], sc0, sc1);
+    act1d_window<V, false>(xw, yv, sc0, sc1, tg, (int64_t)T);
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) {
+      const int qi = side ? V - 3 + qq : qq;
+      if (tg + qi >= 0) y[(base + pad + tg + qi) * 8 + c8] = __float2bfloat16_rn(ch < C ? yv[qi] : 0.f);
+    }
+  }
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int r = lane; r < 2 * pad; r += 32) {
+    const int row = r < pad ? r : T + r;                               // [0, pad) and [pad + T, Tp)
+    *reinterpret_cast<uint4*>(y + (base + row) * 8) = z;
+  }
 }
 
 __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParams P) {
@@ -182,6 +217,11 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
       reinterpret_cast<__half*>(dnm)[((k >> 3) * 32 + n) * 8 + (k & 7)] = __float2half_rn(g);
     }
     fence_async_smem();
+  }
+  // edge rows / zero frame of every (chunk, utterance): one unit per warp, grid-strided over all warps of the grid
+  for (int u = blockIdx.x * (kTThreads / 32) + warp; u < P.nb * P.chunks; u += gridDim.x * (kTThreads / 32)) {
+    const int b = u / P.chunks, chunk = u - b * P.chunks;
+    act1d_edge_unit(P.y, P.x, P.alpha, P.beta, P.C, P.chunks, rows_of(P.lens, P.len_mul, b, P.T), P.Tp, P.pad, chunk, b, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -523,10 +563,11 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
           const int tr0 = (it.grp * P.nseg + s) * P.RL;
           if (s < P.nseg && cc < it.cps_t && tr0 < it.T) {
             const int row0 = tr0 + 128 * g;
-            const int nrows = min(128, min(it.T, tr0 + P.RL) - row0);
-            if (nrows > 0)
-              bulk_s2g(ybase + ((int64_t)(it.tile * P.cps + cc) * P.Tp + P.pad + row0) * 8, obuf + (size_t)sL * kTOutPitch * 16,
-                       (uint32_t)nrows * 16u);
+            // (rows 0..2 and T-3..T-1 belong to the exact edge pass of the prologue)
+            const int lo = max(row0, 3), hi = min(min(row0 + 128, min(it.T, tr0 + P.RL)), it.T - 3);
+            if (hi > lo)
+              bulk_s2g(ybase + ((int64_t)(it.tile * P.cps + cc) * P.Tp + P.pad + lo) * 8,
+                       obuf + ((size_t)sL * kTOutPitch + (lo - row0)) * 16, (uint32_t)(hi - lo) * 16u);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -547,42 +588,6 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
   }
 }
 
-// The rows the tensor-core pass cannot get right plus the tensor's zero frame (see the header): y[0..2], y[T-3..T-1] with
-// the exact replicate-pad semantics, zero halo rows, zero padding channels.  One warp per (chunk, utterance).
-__global__ void __launch_bounds__(32) act1d_c8t_edge_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
-                                                            const float* __restrict__ alpha_log, const float* __restrict__ beta_log,
-                                                            int C, int chunks, int T, int Tp, int pad, const int* __restrict__ lens,
-                                                            int len_mul) {
-  const int chunk = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
-  if (lens) T = lens[b] * len_mul;
-  const int64_t base = ((int64_t)b * chunks + chunk) * Tp;
-  if (lane < 16) {
-    constexpr int V = 8;
-    const int side = lane >> 3, c8 = lane & 7;
-    const int ch = chunk * 8 + c8;
-    const int64_t tg = side ? T - V : 0;
-    float xw[V + 16], yv[V];
-#pragma unroll
-    for (int i = 0; i < V + 16; ++i) {
-      const int64_t t = tg - 8 + i;
-      xw[i] = (t >= 0 && t < T) ? __bfloat162float(x[(base + pad + t) * 8 + c8]) : 0.f;
-    }
-    float sc0 = 0.f, sc1 = 0.f;
-    if (ch < C) snake_params<false>(alpha_log[ch], beta_log[ch], sc0, sc1);
-    act1d_window<V, false>(xw, yv, sc0, sc1, tg, (int64_t)T);
-#pragma unroll
-    for (int qq = 0; qq < 3; ++qq) {
-      const int qi = side ? V - 3 + qq : qq;
-      y[(base + pad + tg + qi) * 8 + c8] = __float2bfloat16_rn(ch < C ? yv[qi] : 0.f);
-    }
-  }
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  for (int r = lane; r < 2 * pad; r += 32) {
-    const int row = r < pad ? r : T + r;                               // [0, pad) and [pad + T, Tp)
-    *reinterpret_cast<uint4*>(y + (base + row) * 8) = z;
-  }
-}
-
 }  // namespace
 
 // Tensor-core Activation1d (see the header).  BVG_ERR_STATE (nothing launched) when the tensor does not qualify; the caller
@@ -595,8 +600,11 @@ int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const fl
   P.bstride = x.batch_stride();
   P.lens = x.lens; P.len_mul = x.len_mul;
   const int ch = x.chunks;
-  if (ch % 16 == 0 || ch > 16) { P.cps = 16; P.sps = 16; }
-  else if (ch % 8 == 0) { P.cps = 8; P.sps = 8; }
+  // the largest tile of 16 / 8 / 4 chunks that divides the chunk count fills all 128 TMEM lanes (C = 192: 24 chunks = 3 tiles
+  // of 8 chunks x 2 time segments, not 16 + a half-empty 8); otherwise 16-chunk tiles with a ragged last one
+  if (ch % 16 == 0) { P.cps = 16; P.sps = 16; }
+  else if (ch % 8 == 0 && BVG_ENV_ONCE("BVG_ACT_TC_SPLIT8", 1)) { P.cps = 8; P.sps = 8; }
+  else if (ch > 16) { P.cps = 16; P.sps = 16; }
   else if (ch % 4 == 0) { P.cps = 4; P.sps = 4; }
   else { P.cps = ch; P.sps = ch <= 4 ? 4 : ch <= 8 ? 8 : 16; }
   P.nseg = 16 / P.sps;
@@ -615,6 +623,8 @@ int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const fl
   const int64_t items = B * P.ntile * P.NG;
   BVG_CHECK_ARG(items < (1ll << 31), "act1d_tc: too many work items");
   P.nitems = (int)items;
+  BVG_CHECK_ARG(B * (int64_t)x.chunks < (1ll << 31), "act1d_tc: too many (chunk, utterance) units");
+  P.nb = (int)B;
   P.dbg = g_dbg_buf;
   P.dry = 0;
 #ifdef BVG_DEBUG
@@ -626,12 +636,6 @@ int act1d_tc_launch(const C8T& y, const C8T& x, const float* alpha_log, const fl
   {
     ProfScope prof(st, KC_ACT1D);
     act1d_tc_kernel<<<(unsigned)std::min<int64_t>(items, num_sms), kTThreads, smem, st>>>(P);
-    BVG_LAUNCHED();
-  }
-  BVG_CHECK_ARG(B <= 65535, "act1d_tc: batch too large for the edge pass grid");
-  {
-    ProfScope prof(st, KC_ACT1D);
-    act1d_c8t_edge_kernel<<<dim3((unsigned)x.chunks, (unsigned)B), 32, 0, st>>>(y.p, x.p, alpha_log, beta_log, x.C, x.chunks, x.T, x.Tp, x.pad, x.lens, x.len_mul);
     BVG_LAUNCHED();
   }
   return BVG_OK;

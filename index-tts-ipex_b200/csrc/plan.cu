@@ -482,7 +482,8 @@ int fused_act_conv(const UmmaLayer& L, const C8T& x, const float* alpha, const f
                    int64_t B, void* scratch, cudaStream_t st) {
   if (!g_fuse_act) return BVG_ERR_STATE;
   // (C = 24 still runs faster on the CUDA-core stencil kernel: BVG_FUSE_TC_MINC, measured in profiles/README.md)
-  if (g_fuse_tc && L.Cin >= BVG_ENV_ONCE("BVG_FUSE_TC_MINC", 48)) {
+  const bool big = B * (int64_t)L.Cin * x.T >= (int64_t)BVG_ENV_ONCE("BVG_FUSE_TC_MIN_MELEMS", 10) * 1000000;   // (as act1d_c8t_launch)
+  if (g_fuse_tc && big && L.Cin >= BVG_ENV_ONCE("BVG_FUSE_TC_MINC", 48)) {
     const int rc = actconv_tc_launch(L, x, alpha, beta, y, ep, B, scratch, st);
     if (rc != BVG_ERR_STATE) return rc;
   }
