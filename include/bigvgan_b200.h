@@ -122,6 +122,11 @@ BVG_API int bvg_act1d_c8t_impl_fwd(void* dst, const void* src, const float* alph
  * (148 CTAs max) into this device buffer: producer wait, MMA waits on input / weights / TMEM, MMA issue,
  * MMA-thread total, epilogue wait, epilogue busy. */
 BVG_API void bvg_debug_set_umma_counters(long long* dev_buf);
+/* Kernel selection of the bf16 path: c8t tensors with fewer than `melems` million elements (B * C * T) run Activation1d / the
+ * fused Activation1d -> Conv1d on the CUDA-core stencil kernels (a single utterance: lower latency), larger ones on the
+ * tensor-core FIR kernels.  Default 10 (env BVG_TC_MIN_MELEMS); 0 = tensor cores whenever the shape qualifies; < 0 restores
+ * the default.  Process-wide. */
+BVG_API void bvg_debug_set_tc_min_melems(int melems);
 /* Activation1d(src) -> Conv1d (+bias, +res1, *scale) in ONE kernel (narrow layers, Cout <= 128): the form the
  * bf16 decode path uses for AMPBlock1's act->conv pairs (models.py:65-74).  Plain [B,C,T] bf16 in/out; status 3
  * when the shape does not qualify.  Test entry point (allocates temporaries). */

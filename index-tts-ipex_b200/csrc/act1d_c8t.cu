@@ -192,7 +192,7 @@ int act1d_c8t_launch(const C8T& y, const C8T& x, const float* alpha_log, const f
   // tensor-core FIRs (act1d_tc.cu) for everything but short tensors; BVG_ACT_TC=0 keeps the CUDA-core stencil (A/B runs)
   // (small problems -- a single utterance -- stay on the stencil kernel: the persistent tensor-core kernel needs ~25 us
   // whatever the size, the stencil 13-22 us for one 10 s utterance; profiles/r02_act1d_tc_shapes.txt)
-  const bool big = B * (int64_t)x.C * x.T >= (int64_t)BVG_ENV_ONCE("BVG_ACT_TC_MIN_MELEMS", 10) * 1000000;
+  const bool big = B * (int64_t)x.C * x.T >= (int64_t)tc_min_melems() * 1000000;
   if (impl == 2 || (impl == 0 && big && BVG_ENV_ONCE("BVG_ACT_TC", 1))) {
     const int rc = act1d_tc_launch(y, x, alpha_log, beta_log, B, st);
     if (rc != BVG_ERR_STATE) return rc;

@@ -74,6 +74,8 @@ inline int smem_opt_in(Kern kern, std::atomic<uint64_t>& done_mask, int bytes) {
   }
   return BVG_OK;
 }
+// size threshold (million elements) below which the c8t Activation1d / fused kernels stay on the CUDA-core stencil (plan.cu)
+int tc_min_melems();
 // SM count of the current device (cached per device; plan.cu)
 int current_device_sms(int* sms);
 // integer environment switch, read ONCE per process per call site (tuning knobs only)

@@ -22,6 +22,14 @@ namespace bvg {
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
 long long* g_dbg_buf = nullptr;
+// tensors below this many million elements stay on the CUDA-core stencil kernels (BVG_TC_MIN_MELEMS, default 10: a single 10 s
+// utterance); bvg_debug_set_tc_min_melems overrides it (tests: the same kernels for single and batched decodes)
+static std::atomic<int> g_tc_min_melems{-1};
+int tc_min_melems() {
+  int v = g_tc_min_melems.load(std::memory_order_relaxed);
+  if (v < 0) { v = env_int_once("BVG_TC_MIN_MELEMS", 10); g_tc_min_melems.store(v, std::memory_order_relaxed); }
+  return v;
+}
 
 // profiler state (per calling thread)
 struct ProfRec { int kc; cudaEvent_t a, b; };
@@ -482,7 +490,7 @@ int fused_act_conv(const UmmaLayer& L, const C8T& x, const float* alpha, const f
                    int64_t B, void* scratch, cudaStream_t st) {
   if (!g_fuse_act) return BVG_ERR_STATE;
   // (C = 24 still runs faster on the CUDA-core stencil kernel: BVG_FUSE_TC_MINC, measured in profiles/README.md)
-  const bool big = B * (int64_t)L.Cin * x.T >= (int64_t)BVG_ENV_ONCE("BVG_FUSE_TC_MIN_MELEMS", 10) * 1000000;   // (as act1d_c8t_launch)
+  const bool big = B * (int64_t)L.Cin * x.T >= (int64_t)tc_min_melems() * 1000000;   // (as act1d_c8t_launch)
   if (g_fuse_tc && big && L.Cin >= BVG_ENV_ONCE("BVG_FUSE_TC_MINC", 48)) {
     const int rc = actconv_tc_launch(L, x, alpha, beta, y, ep, B, scratch, st);
     if (rc != BVG_ERR_STATE) return rc;
@@ -588,6 +596,8 @@ const char* bvg_last_error(void) { return g_error.c_str(); }
 const char* bvg_version(void) { return "bigvgan_b200 0.1 sm_100a"; }
 int64_t bvg_launch_count(void) { return g_launches; }
 void bvg_launch_count_reset(void) { g_launches = 0; }
+
+void bvg_debug_set_tc_min_melems(int melems) { bvg::g_tc_min_melems.store(melems < 0 ? -1 : melems); }
 
 void bvg_profile_begin(void) {
   g_prof_on = true;

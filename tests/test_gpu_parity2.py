@@ -331,6 +331,15 @@ def test_varlen_batch_equals_single_decodes(P):
     what infer_fast lacks, infer.py:480-503): each waveform is bit-equal to decoding that utterance alone (all lengths
     >= 64 latent frames, so the single decodes take the same kernels), and the tail of every row is zero."""
     m, h = _full_model(P)
+    # the single decodes must take the kernels the batch takes (by default small tensors stay on the stencil kernels)
+    P.capi.lib().bvg_debug_set_tc_min_melems(0)
+    try:
+        _varlen_bit_equal(P, m, h)
+    finally:
+        P.capi.lib().bvg_debug_set_tc_min_melems(-1)
+
+
+def _varlen_bit_equal(P, m, h):
     lens = [235, 64, 100, 181, 77, 128, 99]
     lat, mel = O.synthetic_inputs(h, len(lens), max(lens), 40, seed=11)
     lat, mel = lat.cuda(), mel.cuda()
