@@ -510,6 +510,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       const uint32_t upl_lo = (smem_u32(up_lo) >> 4) | (64u << 16);
       const uint32_t xs_lo = (smem_u32(xsm) >> 4) | (8u << 16);
       Ring xr, ur; uint32_t xrdy_ph = 0, xfull_ph = 0, tr_nb = 0;
+      // U barriers are indexed by BLOCK parity (= the snake group that takes the block), U buffers by block % nu: every
+      // waiter then sees every phase of its barrier whatever the ring depth (1 buffer for C = 24, 2-3 otherwise)
+      uint32_t nbk = 0;
+      const uint32_t nu_ = (uint32_t)P.nu;
       long long dbg_wx = 0, dbg_wu = 0;
       const long long dbg_start = P.dbg ? clock64() : 0;
       unsigned long long dbg_ns0 = 0;
@@ -526,7 +530,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             else { tc_wait<0>(&x_full[xr.s], (xfull_ph >> xr.s) & 1u, 4); xfull_ph ^= 1u << xr.s; }
             DBG_ADD(dbg_wx);
           }
-          { DBG_T0(); tc_wait<0>(&u_free[ur.s], ur.ph ^ 1, 5); DBG_ADD(dbg_wu); }
+          if (nbk >= nu_) {                                            // the buffer's previous block (nbk - nu) was read out
+            const uint32_t pb = nbk - nu_;
+            DBG_T0(); tc_wait<0>(&u_free[pb & 1u], (pb >> 1) & 1u, 5); DBG_ADD(dbg_wu);
+          }
           tc_fence_after();
           TCF_TRACE(0, tr_nb); ++tr_nb;
           const uint32_t d = tmem_base + kColU + (uint32_t)ur.s * 64u;
@@ -537,7 +544,8 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
             umma_ss_elect<kAHi, 0x4008u>(d, a0 + 16u * s, uph_lo + 128u * s, idesc_up, s > 0 ? 1u : 0u);
             umma_ss_elect<kAHi, 0x4008u>(d, a0 + 16u * s, upl_lo + 128u * s, idesc_up, 1u);
           }
-          umma_commit_elect(&u_full[ur.s]);
+          umma_commit_elect(&u_full[nbk & 1u]);
+          ++nbk;
           if (pos == kXB - 1 || nu == nup - 1) { umma_commit_elect(&x_free[xr.s]); xr.next(P.nxs); }
           ur.next(P.nu);
         }
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         afree_ph ^= 1u << sl;
         if ((int)(nb & 1u) != grp) continue;
         if (leader) {
-          { DBG_T0(); tc_wait<0>(&u_full[ur.s], ur.ph, 13); DBG_ADD(dbg_su); }
+          { DBG_T0(); tc_wait<0>(&u_full[grp], (nb >> 1) & 1u, 13); DBG_ADD(dbg_su); }   // (barrier = block parity, buffer = ur.s)
           { DBG_T0(); tc_wait<0>(&a_free[sl], aph ^ 1u, 14); DBG_ADD(dbg_sa); }
         }
         if (grp) named_bar_sync(4, 192); else named_bar_sync(1, 192);
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         tmem_ld_wait();                                                // U is in registers: the buffer can be rewritten
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&u_free[ur.s]);
+        if (lane == 0) mbar_arrive(&u_free[grp]);
         half_step(v0, acol);
         half_step(v1, acol + 8u);
         if (warp == 0) TCF_TRACE(2, nb);
@@ -961,8 +969,9 @@ int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, 
   // overlaps the MMAs of tile n + 1), so C = 96 / 48 run U 2 x 64 | A 4 x 32 | Y 2 x 32 | conv 2 x 96.
   if (P.S * P.NB <= 96 && BVG_ENV_ONCE("BVG_TCF_NACC", 2) == 2) { P.nacc = 2; P.nu = 2; P.ny = 2; }
   else if (P.S * P.NB <= 96) { P.nacc = 1; P.nu = 3; P.ny = 3; }
+  else if (BVG_ENV_ONCE("BVG_TCF_NACC24", 2) == 2) { P.nacc = 2; P.nu = 1; P.ny = 2; }   // C = 24: U 64 | A 128 | Y 64 | conv 2 x 128
   else { P.nacc = 1; P.nu = 2; P.ny = 4; }
-  if (const int e = BVG_ENV_ONCE("BVG_TCF_NU", 0)) P.nu = std::min(kMaxNU, std::max(2, e));     // (experiments)
+  if (const int e = BVG_ENV_ONCE("BVG_TCF_NU", 0)) P.nu = std::min(kMaxNU, std::max(1, e));     // (experiments)
   if (const int e = BVG_ENV_ONCE("BVG_TCF_NY", 0)) P.ny = std::min(kMaxNY, std::max(2, e));
   P.colA = (uint32_t)P.nu * 64u; P.colY = P.colA + 128u; P.colC = P.colY + (uint32_t)P.ny * 32u;
   if (P.colC + (uint32_t)(P.nacc * P.S * P.NB) > 512u) return BVG_ERR_STATE;

@@ -489,9 +489,9 @@ const bool g_fuse_tc = [] { const char* e = getenv("BVG_FUSE_TC"); return !(e &&
 int fused_act_conv(const UmmaLayer& L, const C8T& x, const float* alpha, const float* beta, const C8T& y, const UmmaEpilogue& ep,
                    int64_t B, void* scratch, cudaStream_t st) {
   if (!g_fuse_act) return BVG_ERR_STATE;
-  // (C = 24 still runs faster on the CUDA-core stencil kernel: BVG_FUSE_TC_MINC, measured in profiles/README.md)
+  // (BVG_FUSE_TC_MINC: narrowest layer that takes the tensor-core FIR kernel; A/B measurements)
   const bool big = B * (int64_t)L.Cin * x.T >= (int64_t)tc_min_melems() * 1000000;   // (as act1d_c8t_launch)
-  if (g_fuse_tc && big && L.Cin >= BVG_ENV_ONCE("BVG_FUSE_TC_MINC", 48)) {
+  if (g_fuse_tc && big && L.Cin >= BVG_ENV_ONCE("BVG_FUSE_TC_MINC", 24)) {
     const int rc = actconv_tc_launch(L, x, alpha, beta, y, ep, B, scratch, st);
     if (rc != BVG_ERR_STATE) return rc;
   }
