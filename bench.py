@@ -252,6 +252,36 @@ def latency_b1(m, O, h, torch, dev):
     return res
 
 
+def ragged_batch(m, O, h, torch, dev):
+    """32 utterances of DISTINCT lengths (3.4 .. 10 s) in one bvg_decode_varlen call, against decoding them
+    one by one (what equal-length grouping degenerates to) and against padding all of them to the longest."""
+    lens = [80 + 5 * i for i in range(32)]
+    lat, mel = O.synthetic_inputs(h, 32, max(lens), TM, seed=7)
+    lat, mel = lat.to(dev), mel.to(dev)
+    spk = m.speaker_embed(mel)
+    audio_s = sum(lens) * UP / SR
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    seqs = [lat[i, :n].contiguous() for i, n in enumerate(lens)]
+    ms_var = timed(lambda: m.decode_varlen(lat, spk=spk, lens=lens, pcm16=True))
+    ms_one = timed(lambda: [m.decode(s[None], spk=spk[i:i + 1], pcm16=True) for i, s in enumerate(seqs)], n=2)
+    ms_pad = timed(lambda: m.decode(lat, spk=spk, pcm16=True))
+    return {"lens_frames": [lens[0], lens[-1]], "audio_s": audio_s,
+            "one_call_varlen": {"ms": ms_var, "audio_s_per_s": audio_s * 1e3 / ms_var},
+            "one_by_one": {"ms": ms_one, "audio_s_per_s": audio_s * 1e3 / ms_one},
+            "padded_to_longest_wrong_edges": {"ms": ms_pad, "audio_s_per_s": audio_s * 1e3 / ms_pad}}
+
+
 def cpu_reference_rate(frames, threads=None, warm_frames=16):
     """audio-s/s of the oracle port (the reference's algorithm in torch fp32 on the host cores)."""
     import torch
@@ -425,13 +455,13 @@ def run_ours(args):
             print(f"bench: warning: {fus_n} fused launches, accounting expects {work['fused_launches']}", file=sys.stderr)
         if dom == "actconv":
             # algorithmic bytes per launch / average launch time; traffic = ncu dram bytes per launch (same step)
-            roof = {"kernel": "fused Activation1d -> Conv1d of the narrow stages: actconv_tc_kernel (tensor-core FIRs, C = 96 / 48) + "
-                              "conv_umma_fused_kernel (C = 24)", "bound": "hbm",
+            roof = {"kernel": "actconv_tc_kernel: fused Activation1d -> Conv1d of the narrow stages (C = 96 / 48 / 24), both anti-alias "
+                              "FIRs and the conv on tcgen05", "bound": "hbm",
                     "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": fus_gbs / pk["hbm"],
                     "traffic": measured_traffic("actconv")[0], "algorithmic_bytes_per_launch": work["fused_bytes"] / max(fus_n, 1),
                     "traffic_note": measured_traffic("actconv")[1],
-                    "limiter": "instruction issue of the snake / store / epilogue warps (actconv_tc_kernel) and the FMA pipe "
-                               "(conv_umma_fused_kernel), not HBM: see profiles/README.md"}
+                    "limiter": "instruction issue of the snake / store / epilogue warps (85 % of the issue slots on the three SM "
+                               "sub-partitions that own the FIR lanes), not HBM: see profiles/README.md, round 2"}
         elif dom == "act1d":
             roof = {"kernel": "act1d_c8t_kernel", "bound": "hbm", "achieved": act_gbs, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": act_gbs / pk["hbm"], "traffic": None}
@@ -448,7 +478,8 @@ def run_ours(args):
         if not args.no_extras and world == 1:
             ex_sampler = ClockSampler(local)
             ex_sampler.start()
-            extras = {"latency_b1_10s": latency_b1(m, O, h, torch, dev), "act1d_sweep": act1d_sweep(pkg, torch, dev, pk)}
+            extras = {"latency_b1_10s": latency_b1(m, O, h, torch, dev), "act1d_sweep": act1d_sweep(pkg, torch, dev, pk),
+                      "ragged_batch": ragged_batch(m, O, h, torch, dev)}
             extras["clocks"] = ex_sampler.stop()
         cpu_val, cpu_dt, cores = cpu_reference_rate(args.cpu_frames)
         line = {

@@ -40,6 +40,19 @@
 namespace bvg {
 namespace {
 
+// The per-role cycle counters (bvg_debug_set_umma_counters, tools/actconv_tc_roles.py) are compiled in only in debug builds
+// (BVG_DEBUG_BUILD=1): the kernel is instruction-issue bound and the `P.dbg ? clock64() : 0` pairs around every wait cost
+// ~15 instructions per block and role.
+#ifndef BVG_DEBUG
+#undef DBG_T0
+#undef DBG_ADD
+#define DBG_T0() do { } while (0)
+#define DBG_ADD(var) do { } while (0)
+#define TCF_COUNTERS 0
+#else
+#define TCF_COUNTERS 1
+#endif
+
 constexpr int kBlk = 32;                         // output time steps per FIR block
 constexpr int kXB = 2;                           // FIR blocks per staged input tile
 constexpr int kXR = kXB * kBlk + 16;             // rows per chunk of a staged input tile (8-row FIR halo each side)
@@ -515,9 +528,9 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       uint32_t nbk = 0;
       const uint32_t nu_ = (uint32_t)P.nu;
       long long dbg_wx = 0, dbg_wu = 0;
-      const long long dbg_start = P.dbg ? clock64() : 0;
+      const long long dbg_start = (TCF_COUNTERS && P.dbg) ? clock64() : 0;
       unsigned long long dbg_ns0 = 0;
-      if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
+      if (TCF_COUNTERS && P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns0));
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const TcItem it = tc_item(P, item);
         if (it.nblk <= 0) continue;
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           ur.next(P.nu);
         }
       }
-      if (P.dbg && lane == 0) {
+      if (TCF_COUNTERS && P.dbg && lane == 0) {
         long long* d = P.dbg + blockIdx.x * 16;
         d[0] = dbg_wx; d[1] = dbg_wu; d[4] = clock64() - dbg_start;
         unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1)); d[13] = (long long)(ns1 - dbg_ns0);
@@ -595,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           yr.next(P.ny);
         }
       }
-      if (P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[2] = dbg_wa; d[3] = dbg_wy; }
+      if (TCF_COUNTERS && P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[2] = dbg_wa; d[3] = dbg_wy; }
     } else if (warp == kWConv) {
       // ===================== MMA issuer 3: the conv.  D fp32 | A bf16 K-major (A stage) | B bf16 (weights) | N = NB =========
       // The issue loop is latency-bound on the uniform datapath (an MMA whose operands take ~15 dependent uniform instructions
@@ -658,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
           cr.next(nacc);
         }
       }
-      if (P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[9] = dbg_ws; d[10] = dbg_wc; d[11] = dbg_ww; }
+      if (TCF_COUNTERS && P.dbg && lane == 0) { long long* d = P.dbg + blockIdx.x * 16; d[9] = dbg_ws; d[10] = dbg_wc; d[11] = dbg_ww; }
     }
   } else if (warp < kWStore0) {
     // ===================== snake: U (fp32, TMEM) -> a = u + hb - hb cos(2 e^alpha u) -> fp16 pairs (TMEM ring) ==============
@@ -680,11 +693,10 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       if (ch < P.C) snake_params<false>(P.alpha[ch], P.beta[ch], sc0, sc1);
     }
     const f32x2 SC0 = pk2(sc0, sc0), SC1 = pk2(sc1, sc1), NSC1 = pk2(-sc1, -sc1);
-    uint32_t nb = 0;
+    uint32_t mine = 0;                 // blocks this group has taken so far (all items)
     uint32_t afree_ph = 0;
-    Ring ur;
     long long dbg_su = 0, dbg_sa = 0;
-    const long long dbg_sstart = P.dbg ? clock64() : 0;
+    const long long dbg_sstart = (TCF_COUNTERS && P.dbg) ? clock64() : 0;
     auto half_step = [&](const uint32_t (&v)[16], uint32_t dst) {
       uint32_t w[8];
 #pragma unroll
@@ -702,20 +714,23 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
         if (it.nblk <= 0) continue;
+      // every item has an even number of blocks (nblk + 4), so block parity == parity of i: group g takes i = -2 + g, step 2
+      // (A-ring slots sl = i & 3: {2, 0} for group 0, {3, 1} for group 1: each slot's phases are seen by one group only)
       const int iend = it.nblk + 1;
-      for (int i = -2; i <= iend; ++i, ++nb, ur.next(nu)) {
+      for (int i = -2 + grp; i <= iend; i += 2, ++mine) {
         const int sl = i & 3;
-        const uint32_t aph = (afree_ph >> sl) & 1u;
-        afree_ph ^= 1u << sl;
-        if ((int)(nb & 1u) != grp) continue;
+        const uint32_t ubuf = nu == 2 ? (uint32_t)grp : (nu == 1 ? 0u : (2u * mine + (uint32_t)grp) % 3u);
         if (leader) {
-          { DBG_T0(); tc_wait<0>(&u_full[grp], (nb >> 1) & 1u, 13); DBG_ADD(dbg_su); }   // (barrier = block parity, buffer = ur.s)
-          { DBG_T0(); tc_wait<0>(&a_free[sl], aph ^ 1u, 14); DBG_ADD(dbg_sa); }
+          { DBG_T0(); tc_wait<0>(&u_full[grp], mine & 1u, 13); DBG_ADD(dbg_su); }      // (barrier = block parity)
+          { DBG_T0(); tc_wait<0>(&a_free[sl], ((afree_ph >> sl) & 1u) ^ 1u, 14); DBG_ADD(dbg_sa); }
         }
+        afree_ph ^= 1u << sl;
+        const uint32_t nb = 2u * mine + (uint32_t)grp;                 // (global block index: traces only)
+        (void)nb;
         if (grp) named_bar_sync(4, 192); else named_bar_sync(1, 192);
         if (warp == 0) TCF_TRACE(1, nb);
         tc_fence_after();
-        const uint32_t ucol = tq + kColU + (uint32_t)ur.s * 64u + (uint32_t)h * 32u;
+        const uint32_t ucol = tq + kColU + ubuf * 64u + (uint32_t)h * 32u;
         const uint32_t acol = tq + colA + (uint32_t)sl * 32u + (uint32_t)h * 16u;
         uint32_t v0[16], v1[16];
         tmem_ld16_nowait(ucol, v0);
@@ -734,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         if (warp == 0) TCF_TRACE(3, nb);
       }
     }
-    if (P.dbg && threadIdx.x == 0) { long long* d = P.dbg + blockIdx.x * 16; d[5] = dbg_su; d[6] = dbg_sa; d[15] = clock64() - dbg_sstart; }
+    if (TCF_COUNTERS && P.dbg && threadIdx.x == 0) { long long* d = P.dbg + blockIdx.x * 16; d[5] = dbg_su; d[6] = dbg_sa; d[15] = clock64() - dbg_sstart; }
   } else if (warp < kWEpi0) {
     // ===================== store: Y (fp32, TMEM; lane = channel) -> bf16 -> conv A stage(s) in shared memory ===============
     // 6 warps: TMEM lane quarter q = warp % 4 (0..2), 16-step half h of every block.  tcgen05.ld.16x256b returns the mma
@@ -814,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         ++tr_j;
       }
     }
-    if (P.dbg && threadIdx.x == kWStore0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[7] = dbg_ty; d[8] = dbg_tf; }
+    if (TCF_COUNTERS && P.dbg && threadIdx.x == kWStore0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[7] = dbg_ty; d[8] = dbg_tf; }
   } else {
     // ===================== conv epilogue: 8 warps = 2 sets x 4 TMEM lane quarters; every tile is split between the sets =======
     // (the tile's S x NB / 16 column slices are dealt out half and half, so the single accumulator stage drains twice as fast)
@@ -901,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
         cr.next(nacc);
       }
     }
-    if (P.dbg && threadIdx.x == kWEpi0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[12] = dbg_ew; d[14] = dbg_eb; }
+    if (TCF_COUNTERS && P.dbg && threadIdx.x == kWEpi0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[12] = dbg_ew; d[14] = dbg_eb; }
   }
   tc_fence_before();
   __syncthreads();
