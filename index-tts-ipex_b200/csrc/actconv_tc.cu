@@ -784,50 +784,66 @@ __global__ void __launch_bounds__(kThreads, 1) actconv_tc_kernel(const ActConvTc
       asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(ok ? a : dump_a), "r"(pa[0]), "r"(pa[1]), "r"(pa[2]), "r"(pa[3]) : "memory");
       asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(ok ? a + pair_off : dump_a), "r"(pb[0]), "r"(pb[1]), "r"(pb[2]), "r"(pb[3]) : "memory");
     };
+    // One block: wait (the group's polling warp) -> Y from TMEM -> free the Y buffer -> bf16 pairs in pa / pb.
+    uint32_t pa[4], pb[4];
+    auto load_block = [&](bool wait_open) {
+      if (warp == kWStore0) {
+        { DBG_T0(); tc_wait<0>(&y_full[yr.s], yr.ph, 15); DBG_ADD(dbg_ty); }
+        if (wait_open) { DBG_T0(); tc_wait<0>(&as_free[open.s], open.ph ^ 1, 16); DBG_ADD(dbg_tf); }
+      }
+      named_bar_sync(2, 192);
+      if (warp == kWStore0) TCF_TRACE(5, tr_j);
+      tc_fence_after();
+      uint32_t va[8], vb[8];
+      tmem_ld_16x256b_x2_nowait(tqa + (uint32_t)yr.s * 32u, va);
+      tmem_ld_16x256b_x2_nowait(tqb + (uint32_t)yr.s * 32u, vb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&y_free[yr.s]);
+      yr.next(ny);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pa[i] = cvt_bf16x2(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
+        pb[i] = cvt_bf16x2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]));
+      }
+      if (warp == kWStore0) TCF_TRACE(6, tr_j);
+      ++tr_j;
+    };
+    const bool dry = TCF_DRY(32);
+    auto st_main = [&](int p) { if (!dry) stsm2(stage0 + (uint32_t)mainr.s * stage_bytes + main_off + (uint32_t)p * 512u, pa, pb); };
+    auto st_next = [&]() { if (any_next && !dry) stsm2_masked(ok_next, stage0 + (uint32_t)open.s * stage_bytes + next_off, pa, pb); open.next(nas); };
+    auto close_tile = [&](const TcItem& it, int m) {                  // last rows of tile m, then the stage is complete
+      if (any_prev && !dry) stsm2_masked(ok_prev, stage0 + (uint32_t)closer.s * stage_bytes + prev_off, pa, pb);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tile_edge(P, it, m) ? &as_edone[closer.s] : &as_done[closer.s]);
+      closer.next(nas);
+    };
+    // Straight-line per tile (the SM is issue-bound: no per-block case analysis): block -1 opens tile 0's stage; blocks 4n ..
+    // 4n + 3 fill tile n, block 4n also closes tile n - 1, block 4n + 3 opens tile n + 1; block nblk closes the last tile.
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const TcItem it = tc_item(P, item);
-        if (it.nblk <= 0) continue;
-      const int nblk = it.nblk;
-      for (int j = -1; j <= nblk; ++j) {
-        const int p = j & 3;
-        const bool opens = p == 3 && j + 1 < nblk;                     // first rows of tile (j + 1) / 4's stage
-        if (warp == kWStore0) {                                        // one polling warp per role group
-          { DBG_T0(); tc_wait<0>(&y_full[yr.s], yr.ph, 15); DBG_ADD(dbg_ty); }
-          if (opens) { DBG_T0(); tc_wait<0>(&as_free[open.s], open.ph ^ 1, 16); DBG_ADD(dbg_tf); }
-        }
-        named_bar_sync(2, 192);
-        if (warp == kWStore0) TCF_TRACE(5, tr_j);
-        tc_fence_after();
-        uint32_t va[8], vb[8];
-        tmem_ld_16x256b_x2_nowait(tqa + (uint32_t)yr.s * 32u, va);
-        tmem_ld_16x256b_x2_nowait(tqb + (uint32_t)yr.s * 32u, vb);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&y_free[yr.s]);
-        yr.next(ny);
-        uint32_t pa[4], pb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pa[i] = cvt_bf16x2(__uint_as_float(va[2 * i]), __uint_as_float(va[2 * i + 1]));
-          pb[i] = cvt_bf16x2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]));
-        }
-        if (!TCF_DRY(32)) {
-          if (j >= 0 && j < nblk) stsm2(stage0 + (uint32_t)mainr.s * stage_bytes + main_off + (uint32_t)p * 512u, pa, pb);
-          if (opens && any_next) stsm2_masked(ok_next, stage0 + (uint32_t)open.s * stage_bytes + next_off, pa, pb);
-          if (p == 0 && j > 0 && any_prev) stsm2_masked(ok_prev, stage0 + (uint32_t)closer.s * stage_bytes + prev_off, pa, pb);
-        }
-        if (opens) open.next(nas);
-        if (p == 0 && j > 0) {                                         // tile j / 4 - 1 is complete
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tile_edge(P, it, (j >> 2) - 1) ? &as_edone[closer.s] : &as_done[closer.s]);
-          closer.next(nas);
-        }
-        if (p == 3 && j >= 0) mainr.next(nas);
-        if (warp == kWStore0) TCF_TRACE(6, tr_j);
-        ++tr_j;
+      if (it.nblk <= 0) continue;
+      const int ntile = it.nblk >> 2;
+      load_block(true);
+      st_next();
+      for (int n = 0; n < ntile; ++n) {
+        load_block(false);
+        st_main(0);
+        if (n > 0) close_tile(it, n - 1);
+        load_block(false);
+        st_main(1);
+        load_block(false);
+        st_main(2);
+        const bool op = n + 1 < ntile;
+        load_block(op);
+        st_main(3);
+        if (op) st_next();
+        mainr.next(nas);
       }
+      load_block(false);
+      close_tile(it, ntile - 1);
     }
     if (TCF_COUNTERS && P.dbg && threadIdx.x == kWStore0 * 32) { long long* d = P.dbg + blockIdx.x * 16; d[7] = dbg_ty; d[8] = dbg_tf; }
   } else {
