@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libbigvgan_b200.so"
-SOURCES = ["act1d.cu", "act1d_c8t.cu", "act1d_tc.cu", "actconv_tc.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_fused.cu", "mel.cu", "misc.cu", "plan.cu"]
+SOURCES = ["act1d.cu", "act1d_c8t.cu", "act1d_tc.cu", "actconv_tc.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_fused.cu", "ecapa.cu", "mel.cu", "misc.cu", "plan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", 

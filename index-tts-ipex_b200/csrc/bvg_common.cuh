@@ -156,13 +156,26 @@ int cast_to_f32_launch(float* dst, const void* src, int src_dtype, int64_t n, cu
 // y[b,co] = epilogue(sum_ci w[ci][co] x[b,ci]) for contiguous x [B,Cin], y [B,Cout]; w is the K=1 [Cin][Cout] pack
 int matvec_launch(float* y, const float* x, const float* w_ic, const ConvEpilogue& ep, int64_t B, int Cin, int Cout,
                   cudaStream_t st);
+// several such layers over the SAME x in one launch (the speaker-condition vectors of all stages: models.py:226,233-234)
+constexpr int kMaxMatvecJobs = 8;
+struct MatvecJob {
+  const float* w = nullptr;           // [Cin][Cout]
+  const float* bias = nullptr;
+  float* y = nullptr;                 // [B, Cout]
+  int Cout = 0, relu = 0, act = 0;
+  const float* post_scale = nullptr;
+  const float* post_shift = nullptr;
+};
+int matvec_multi_launch(const MatvecJob* jobs, int njobs, const float* x, int64_t B, int Cin, cudaStream_t st);
 // mean over time of each row of x [rows, T] (row r at x + r*T) -> out[r]
 int row_mean_launch(float* out, const float* x, int64_t rows, int64_t T, cudaStream_t st);
 // mean/std over time: x [B,C,T] -> ms[b, c] = mean, ms[b, C + c] = sqrt(clamp(var, 1e-12))
 int row_stats_launch(float* ms, const float* x, int64_t B, int64_t C, int64_t T, cudaStream_t st);
-// out[b,c,t] = s[b,c] * y[b,c,t] + res[b,c,t]; out/res have batch strides osb/rsb, y is contiguous
+// out[b,c,t] = s[b,c] * y[b,c,t] + res[b,c,t]; out/res have batch strides osb/rsb, y is contiguous; yc (optional): the
+// same values as a c8t bf16 tensor (or channel-slice view of one)
+struct C8T;
 int scale_residual_launch(float* out, int64_t osb, const float* s, const float* y, const float* res, int64_t rsb,
-                          int64_t B, int64_t C, int64_t T, cudaStream_t st);
+                          int64_t B, int64_t C, int64_t T, cudaStream_t st, const C8T* yc = nullptr);
 // attentive statistics: softmax over time of logits[b,c,:], weighted mean/std of x[b,c,:], then the
 // eval-BatchNorm affine (scale/shift [2C]):  pooled[b, c], pooled[b, C + c]
 int attn_stats_launch(float* pooled, const float* logits, const float* x, const float* bn_scale,

@@ -312,6 +312,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (j < nj) f[j] += cond[co + j];
               }
+              if (P.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (P.post_scale) {                                     // eval-BatchNorm folded to an affine (ECAPA TDNN)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < nj) f[j] = fmaf(f[j], P.post_scale[co + j], P.post_shift[co + j]);
+              }
+              if (P.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = tanhf(f[j]);
+              }
               if (r1f) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (j < nj) f[j] += r1f[o + (int64_t)j * P.Tout];
@@ -322,6 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) if (j < nj) yfb[o + (int64_t)j * P.Tout] = f[j] * scale;
+              if (P.y && g < nok) {                                   // both forms of the output (speaker encoder: fp32 for the
+                uint4 oc;                                             // statistics, c8t bf16 for the next 1x1 GEMM)
+                oc.x = pack2(f[0] * scale, f[1] * scale); oc.y = pack2(f[2] * scale, f[3] * scale);
+                oc.z = pack2(f[4] * scale, f[5] * scale); oc.w = pack2(f[6] * scale, f[7] * scale);
+                *reinterpret_cast<uint4*>(yb + off0 + g * cs) = oc;
+              }
             }
             continue;
           }
@@ -580,8 +598,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   const int Cin_eff = L.split ? 2 * ((L.Cin + 7) / 8 * 8) : L.Cin;
   const int K_eff = L.split ? 2 * L.K : L.K;
   BVG_CHECK_ARG(!L.split || ep.yf32, "conv_umma: split weights need the fp32 output epilogue");
-  BVG_CHECK_ARG(!ep.yf32 || (!ep.res1 && !ep.res2 && !ep.relu && !ep.post_scale && !ep.act && !ep.zero_pads),
-                "conv_umma: the fp32 output epilogue takes bias / cond / fp32 residuals / scale only");
+  BVG_CHECK_ARG(!ep.yf32 || (!ep.res1 && !ep.res2 && !ep.zero_pads && ep.act <= 1),
+                "conv_umma: the fp32 output epilogue takes bias / cond / ReLU / affine / tanh / fp32 residuals / scale only");
   BVG_CHECK_ARG(x.C == Cin_eff && y.C == L.Cout, "conv_umma: channel mismatch (x.C=%d Cin=%d y.C=%d Cout=%d)", x.C, Cin_eff, y.C, L.Cout);
   UmmaConvParams P;
   memset(&P, 0, sizeof P);
@@ -629,8 +647,8 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
   BVG_CHECK_ARG(x.chunks * 8 >= P.Cin_p, "conv_umma: input tensor must carry channel padding to a multiple of 16");
   P.n_ci_blk = (P.Cin_p + 63) / 64;
   P.Cout = L.Cout;
-  P.x = x.p; P.x_bstride = (int64_t)x.chunks * x.Tp * 8; P.x_tp = x.Tp; P.x_row0 = x.pad;
-  P.y = y.p; P.y_bstride = (int64_t)y.chunks * y.Tp * 8; P.y_tp = y.Tp; P.y_row0 = y.pad; P.y_chunks = y.chunks;
+  P.x = x.p; P.x_bstride = x.batch_stride(); P.x_tp = x.Tp; P.x_row0 = x.pad;
+  P.y = y.p; P.y_bstride = y.batch_stride(); P.y_tp = y.Tp; P.y_row0 = y.pad; P.y_chunks = y.chunks;
   P.lens = y.lens; P.len_mul = y.len_mul;
   BVG_CHECK_ARG(!y.lens || !ep.yf32, "conv_umma: ragged batches are a bf16 c8t feature");
   P.w = L.w;

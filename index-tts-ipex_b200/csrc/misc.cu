@@ -1,7 +1,10 @@
 // Small reduction / elementwise kernels of the decode path (speaker encoder glue, conv_post).
 // References: ECAPA_TDNN.py:228-242 (SEBlock), :282-338 (AttentiveStatisticsPooling),
 // models.py:246-248 (activation_post -> conv_post -> tanh), infer.py:206-212 (int16 epilogue).
+#include <string.h>
+
 #include "bvg_common.cuh"
+#include "umma.cuh"
 
 namespace bvg {
 namespace {
@@ -47,13 +50,33 @@ __global__ void row_stats_kernel(float* __restrict__ ms, const float* __restrict
   }
 }
 
+// one thread = 8 channels (one c8t chunk) of one time step: fp32 out and, when yc is given, the same values as one 16-byte
+// row of the c8t bf16 tensor the next 1x1 GEMM reads
 __global__ void scale_residual_kernel(float* __restrict__ out, int64_t osb, const float* __restrict__ s,
                                       const float* __restrict__ y, const float* __restrict__ res, int64_t rsb,
-                                      int64_t B, int64_t C, int64_t T) {
-  const int64_t n = B * C * T;
+                                      int64_t B, int64_t C, int64_t T, __nv_bfloat16* __restrict__ yc, int64_t yc_bstride,
+                                      int yc_tp, int yc_pad) {
+  const int64_t C8 = (C + 7) / 8, n = B * C8 * T;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i % T, c = (i / T) % C, b = i / (T * C);
-    out[b * osb + c * T + t] = fmaf(s[b * C + c], y[i], res[b * rsb + c * T + t]);
+    const int64_t t = i % T, c8 = (i / T) % C8, b = i / (T * C8);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t c = c8 * 8 + k;
+      v[k] = 0.f;
+      if (c < C) {
+        v[k] = fmaf(s[b * C + c], y[(b * C + c) * T + t], res[b * rsb + c * T + t]);
+        out[b * osb + c * T + t] = v[k];
+      }
+    }
+    if (yc) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+      o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(yc + b * yc_bstride + (c8 * yc_tp + yc_pad + t) * 8) = o;
+    }
   }
 }
 
@@ -86,32 +109,54 @@ __global__ void attn_stats_kernel(float* __restrict__ pooled, const float* __res
 // y[b, co] = epilogue(sum_ci w[ci][co] * x[b, ci]): the T == 1 "convs" of the path (cond vectors, SE block,
 // attentive-statistics context, final fc).  256 threads = 64 outputs x 4 input slices; weights are read
 // coalesced along co from the [Cin][Cout] pack, partial sums meet in shared memory.
+struct MatvecJobs {
+  MatvecJob job[kMaxMatvecJobs];
+  int blk0[kMaxMatvecJobs + 1];        // first blockIdx.x of every job
+  int njobs;
+};
+// 256 threads = 32 outputs x 8 input slices, sixteen independent loads in flight per thread (one accumulator chain with four
+// loads per round trip made each of these launches ~25 us of L2 latency); several layers that read the same x share a launch.
 __global__ void __launch_bounds__(256)
-matvec_kernel(float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ w,
-              const float* __restrict__ bias, int relu, const float* __restrict__ post_scale,
-              const float* __restrict__ post_shift, int act, int Cin, int Cout) {
-  __shared__ float part[4][64];
-  const int co = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int sl = threadIdx.x >> 6;
+matvec_kernel(const MatvecJobs J, const float* __restrict__ x, int Cin) {
+  __shared__ float part[8][32];
+  int j = 0;
+  while (j + 1 < J.njobs && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
+  const MatvecJob& job = J.job[j];
+  const int Cout = job.Cout;
+  const int co = ((int)blockIdx.x - J.blk0[j]) * 32 + (threadIdx.x & 31);
+  const int sl = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const float* xb = x + (int64_t)b * Cin;
-  float acc = 0.f;
+  const float* w = job.w;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   if (co < Cout) {
-    const int per = (Cin + 3) / 4;
+    const int per = (Cin + 7) / 8;
     const int lo = sl * per, hi = min(Cin, lo + per);
-#pragma unroll 4
-    for (int ci = lo; ci < hi; ++ci) acc = fmaf(w[(int64_t)ci * Cout + co], xb[ci], acc);
+    int ci = lo;
+    for (; ci + 16 <= hi; ci += 16) {
+      float wv[16], xv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { wv[u] = __ldg(w + (int64_t)(ci + u) * Cout + co); xv[u] = __ldg(xb + ci + u); }
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        acc0 = fmaf(wv[u], xv[u], acc0); acc1 = fmaf(wv[u + 1], xv[u + 1], acc1);
+        acc2 = fmaf(wv[u + 2], xv[u + 2], acc2); acc3 = fmaf(wv[u + 3], xv[u + 3], acc3);
+      }
+    }
+    for (; ci < hi; ++ci) acc0 = fmaf(__ldg(w + (int64_t)ci * Cout + co), __ldg(xb + ci), acc0);
   }
-  part[sl][threadIdx.x & 63] = acc;
+  part[sl][threadIdx.x & 31] = (acc0 + acc1) + (acc2 + acc3);
   __syncthreads();
   if (sl == 0 && co < Cout) {
-    float v = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
-    if (bias) v += bias[co];
-    if (relu) v = fmaxf(v, 0.f);
-    if (post_scale) v = fmaf(v, post_scale[co], post_shift[co]);
-    if (act == 1) v = tanhf(v);
-    if (act == 2) v = 1.f / (1.f + expf(-v));
-    y[(int64_t)b * Cout + co] = v;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][threadIdx.x];
+    if (job.bias) v += job.bias[co];
+    if (job.relu) v = fmaxf(v, 0.f);
+    if (job.post_scale) v = fmaf(v, job.post_scale[co], job.post_shift[co]);
+    if (job.act == 1) v = tanhf(v);
+    if (job.act == 2) v = 1.f / (1.f + expf(-v));
+    job.y[(int64_t)b * Cout + co] = v;
   }
 }
 
@@ -149,17 +194,36 @@ conv_post_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const T* __
 
 }  // namespace
 
+int matvec_multi_launch(const MatvecJob* jobs, int njobs, const float* x, int64_t B, int Cin, cudaStream_t st) {
+  BVG_CHECK_ARG(jobs && x && Cin > 0 && njobs >= 1 && njobs <= kMaxMatvecJobs, "matvec: bad argument");
+  if (B == 0) return BVG_OK;
+  BVG_CHECK_ARG(B <= 65535, "matvec: batch too large");
+  MatvecJobs J;
+  memset(&J, 0, sizeof J);
+  J.njobs = njobs;
+  int blk = 0;
+  for (int j = 0; j < njobs; ++j) {
+    BVG_CHECK_ARG(jobs[j].w && jobs[j].y && jobs[j].Cout > 0, "matvec: bad job");
+    J.job[j] = jobs[j];
+    J.blk0[j] = blk;
+    blk += (jobs[j].Cout + 31) / 32;
+  }
+  J.blk0[njobs] = blk;
+  dim3 grid((unsigned)blk, (unsigned)B);
+  ProfScope prof(st, KC_OTHER);
+  matvec_kernel<<<grid, 256, 0, st>>>(J, x, Cin);
+  BVG_LAUNCHED();
+  return BVG_OK;
+}
+
 int matvec_launch(float* y, const float* x, const float* w_ic, const ConvEpilogue& ep, int64_t B, int Cin, int Cout,
                   cudaStream_t st) {
   BVG_CHECK_ARG(y && x && w_ic && Cin > 0 && Cout > 0, "matvec: bad argument");
   BVG_CHECK_ARG(!ep.res1 && !ep.res2 && !ep.cond && ep.scale == 1.f, "matvec: unsupported epilogue");
-  if (B == 0) return BVG_OK;
-  BVG_CHECK_ARG(B <= 65535, "matvec: batch too large");
-  dim3 grid((unsigned)((Cout + 63) / 64), (unsigned)B);
-  ProfScope prof(st, KC_OTHER);
-  matvec_kernel<<<grid, 256, 0, st>>>(y, x, w_ic, ep.bias, ep.relu, ep.post_scale, ep.post_shift, ep.act, Cin, Cout);
-  BVG_LAUNCHED();
-  return BVG_OK;
+  MatvecJob j;
+  j.w = w_ic; j.bias = ep.bias; j.y = y; j.Cout = Cout; j.relu = ep.relu; j.post_scale = ep.post_scale;
+  j.post_shift = ep.post_shift; j.act = ep.act;
+  return matvec_multi_launch(&j, 1, x, B, Cin, st);
 }
 
 int row_mean_launch(float* out, const float* x, int64_t rows, int64_t T, cudaStream_t st) {
@@ -177,12 +241,14 @@ int row_stats_launch(float* ms, const float* x, int64_t B, int64_t C, int64_t T,
   return BVG_OK;
 }
 int scale_residual_launch(float* out, int64_t osb, const float* s, const float* y, const float* res, int64_t rsb,
-                          int64_t B, int64_t C, int64_t T, cudaStream_t st) {
-  const int64_t n = B * C * T;
+                          int64_t B, int64_t C, int64_t T, cudaStream_t st, const C8T* yc) {
+  const int64_t n = B * ((C + 7) / 8) * T;
   if (n == 0) return BVG_OK;
+  BVG_CHECK_ARG(!yc || (yc->T == (int)T && yc->chunks * 8 >= C), "scale_residual: c8t output geometry");
   int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   ProfScope prof(st, KC_OTHER);
-  scale_residual_kernel<<<blocks, 256, 0, st>>>(out, osb, s, y, res, rsb, B, C, T);
+  scale_residual_kernel<<<blocks, 256, 0, st>>>(out, osb, s, y, res, rsb, B, C, T, yc ? yc->p : nullptr,
+                                                yc ? yc->batch_stride() : 0, yc ? yc->Tp : 0, yc ? yc->pad : 0);
   BVG_LAUNCHED();
   return BVG_OK;
 }

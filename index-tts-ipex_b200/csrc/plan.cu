@@ -321,20 +321,32 @@ int tdnn_f32(float* dst, int64_t dsb, const float* src, const float* src2, int64
   return conv_f32(dst, dsb, src, src2, sb, sc, st_, t.conv, ep, B, T, t.dil, 1, st);
 }
 
-// A 1x1 TDNN layer (a plain GEMM over B*T columns) on the tcgen05 path: fp32 [B,C,T] -> c8t bf16 -> conv_umma with
-// the bias / cond / ReLU / folded-BN / tanh epilogue -> fp32 [B,C,T].  Used by the bf16 decode path only.
-int tdnn_umma(float* dst, const float* src, int64_t sb, int64_t sc, int64_t st_, const ConvLayer& L,
-              const float* bn_scale, const float* bn_shift, int relu, int act, const float* cond, int64_t B, int64_t T,
-              const EcapaWs& w, cudaStream_t st) {
-  C8T x = make_c8t(w.cx, L.Cin, (int)T), y = make_c8t(w.cy, L.Cout, (int)T);
-  BVG_TRY(to_c8t_launch(x, src, sb, sc, st_, BVG_F32, B, st));
+// A 1x1 TDNN layer (a plain GEMM over B*T columns) on the tcgen05 path: c8t bf16 input, bias / cond / ReLU / folded-BN /
+// tanh epilogue, output as fp32 [B,C,T] (dst) and / or c8t bf16 (dstc).  Used by the bf16 decode path only.
+int tdnn_umma(float* dst, const C8T* dstc, const C8T& x, const ConvLayer& L, const float* bn_scale, const float* bn_shift,
+              int relu, int act, const float* cond, int64_t B, int64_t T, cudaStream_t st) {
   UmmaLayer u;
   u.w = L.wu; u.Cin = L.Cin; u.Cout = L.Cout; u.K = 1; u.dil = 1;
   UmmaEpilogue ep;
   ep.bias = L.bias; ep.cond = cond; ep.cond_B = B; ep.relu = relu; ep.post_scale = bn_scale; ep.post_shift = bn_shift;
-  ep.act = act; ep.prof_other = 1;
-  BVG_TRY(conv_umma_launch(u, x, y, ep, B, st));
-  return from_c8t_launch(dst, y, BVG_F32, B, st);
+  ep.act = act; ep.prof_other = 1; ep.yf32 = dst;
+  return conv_umma_launch(u, x, dstc ? *dstc : make_c8t(nullptr, L.Cout, (int)T), ep, B, st);
+}
+
+// Res2NetBlock (ECAPA_TDNN.py:179-191) through ecapa.cu's chain kernel when the block has its standard geometry
+int res2net_chain(const SERes2& S, const float* y1, float* y2, const C8T* yc, int64_t B, int64_t T, bool* taken,
+                  cudaStream_t st) {
+  *taken = false;
+  if (BVG_ENV_ONCE("BVG_ECAPA_CHAIN", 1) == 0) return BVG_OK;
+  const float *w[7], *bias[7], *sc[7], *sh[7];
+  for (int j = 0; j < 7; ++j) {
+    const Tdnn& t = S.r2n[j];
+    if (t.conv.K != 3 || t.conv.Cin != kEC / 8 || t.conv.Cout != kEC / 8 || t.dil != S.r2n[0].dil || !t.conv.bias ||
+        !t.bn_scale || !t.bn_shift)
+      return BVG_OK;
+    w[j] = t.conv.w; bias[j] = t.conv.bias; sc[j] = t.bn_scale; sh[j] = t.bn_shift;
+  }
+  return res2net_chain_launch(y1, y2, yc, w, bias, sc, sh, S.r2n[0].dil, B, T, taken, st);
 }
 
 // ECAPA_TDNN.forward (ECAPA_TDNN.py:543-581), lengths=None.  mel [Bm,Tm,num_mels] -> spk [Bm,E]
@@ -346,20 +358,38 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
   BVG_TRY(tdnn_f32(w.X0, kEC * Tm, mel, nullptr, Tm * NM, 1, NM, P->e_block0, Bm, Tm, st));
   const float* X = w.X0;
   int64_t Xsb = kEC * Tm;
+  // tensor-core path: activations meet the 1x1 GEMMs as c8t bf16 tensors written by their producers (no fp32 -> c8t ->
+  // fp32 round trips): XLc = the three block outputs side by side (the MFA input), Mc = the MFA output; the block-0
+  // output, the Res2Net chain output and the attention hidden layer borrow whichever of the two is idle.
+  C8T XLc = make_c8t(w.cx, kEM, (int)Tm), Mc = make_c8t(w.cy, kEM, (int)Tm);
+  C8T X0c = make_c8t(w.cy, kEC, (int)Tm);
+  C8T Y2c = make_c8t(static_cast<char*>(w.cy) + c8t_bytes(Bm, kEC, Tm), kEC, (int)Tm);
+  C8T A1c = make_c8t(w.cx, kEA, (int)Tm);
+  auto xl_slice = [&](int i) {                                   // channels [512 i, 512 (i + 1)) of XLc
+    C8T v = make_c8t(XLc.p + (int64_t)i * (kEC / 8) * XLc.Tp * 8, kEC, (int)Tm);
+    v.bstride = XLc.batch_stride();
+    return v;
+  };
+  if (tc) BVG_TRY(to_c8t_launch(X0c, w.X0, kEC * Tm, Tm, 1, BVG_F32, Bm, st));
   for (int i = 0; i < 3; ++i) {
     const SERes2& S = P->e_blk[i];
-    if (tc) BVG_TRY(tdnn_umma(w.Y1, X, Xsb, Tm, 1, S.tdnn1.conv, S.tdnn1.bn_scale, S.tdnn1.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+    if (tc) BVG_TRY(tdnn_umma(w.Y1, nullptr, i == 0 ? X0c : xl_slice(i - 1), S.tdnn1.conv, S.tdnn1.bn_scale, S.tdnn1.bn_shift, 1, 0, nullptr, Bm, Tm, st));
     else BVG_TRY(tdnn_f32(w.Y1, kEC * Tm, X, nullptr, Xsb, Tm, 1, S.tdnn1, Bm, Tm, st));
     // Res2NetBlock :179-191: 8 chunks of 64 channels, y_i = f(x_i + y_{i-1})
     const int CH = kEC / 8;
-    BVG_CUDA(cudaMemcpy2DAsync(w.Y2, kEC * Tm * 4, w.Y1, kEC * Tm * 4, (size_t)CH * Tm * 4, Bm,
-                               cudaMemcpyDeviceToDevice, st));
-    for (int j = 1; j < 8; ++j) {
-      const float* s2 = (j >= 2) ? w.Y2 + (int64_t)(j - 1) * CH * Tm : nullptr;
-      BVG_TRY(tdnn_f32(w.Y2 + (int64_t)j * CH * Tm, kEC * Tm, w.Y1 + (int64_t)j * CH * Tm, s2, kEC * Tm, Tm, 1,
-                       S.r2n[j - 1], Bm, Tm, st));
+    bool chained = false;
+    BVG_TRY(res2net_chain(S, w.Y1, tc ? nullptr : w.Y2, tc ? &Y2c : nullptr, Bm, Tm, &chained, st));   // one cluster launch
+    if (!chained) {
+      BVG_CUDA(cudaMemcpy2DAsync(w.Y2, kEC * Tm * 4, w.Y1, kEC * Tm * 4, (size_t)CH * Tm * 4, Bm,
+                                 cudaMemcpyDeviceToDevice, st));
+      for (int j = 1; j < 8; ++j) {
+        const float* s2 = (j >= 2) ? w.Y2 + (int64_t)(j - 1) * CH * Tm : nullptr;
+        BVG_TRY(tdnn_f32(w.Y2 + (int64_t)j * CH * Tm, kEC * Tm, w.Y1 + (int64_t)j * CH * Tm, s2, kEC * Tm, Tm, 1,
+                         S.r2n[j - 1], Bm, Tm, st));
+      }
+      if (tc) BVG_TRY(to_c8t_launch(Y2c, w.Y2, kEC * Tm, Tm, 1, BVG_F32, Bm, st));
     }
-    if (tc) BVG_TRY(tdnn_umma(w.Y3, w.Y2, kEC * Tm, Tm, 1, S.tdnn2.conv, S.tdnn2.bn_scale, S.tdnn2.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+    if (tc) BVG_TRY(tdnn_umma(w.Y3, nullptr, Y2c, S.tdnn2.conv, S.tdnn2.bn_scale, S.tdnn2.bn_shift, 1, 0, nullptr, Bm, Tm, st));
     else BVG_TRY(tdnn_f32(w.Y3, kEC * Tm, w.Y2, nullptr, kEC * Tm, Tm, 1, S.tdnn2, Bm, Tm, st));
     // SEBlock :228-242
     BVG_TRY(row_mean_launch(w.sem, w.Y3, Bm * kEC, Tm, st));
@@ -368,10 +398,11 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
     ConvEpilogue e2; e2.act = 2;
     BVG_TRY(conv_f32(w.se2, kEC, w.se1, nullptr, kEA, 1, 1, S.se2, e2, Bm, 1, 1, 0, st));
     float* out = w.XL + (int64_t)i * kEC * Tm;
-    BVG_TRY(scale_residual_launch(out, kEM * Tm, w.se2, w.Y3, X, Xsb, Bm, kEC, Tm, st));
+    C8T outc = xl_slice(i);
+    BVG_TRY(scale_residual_launch(out, kEM * Tm, w.se2, w.Y3, X, Xsb, Bm, kEC, Tm, st, tc ? &outc : nullptr));
     X = out; Xsb = kEM * Tm;
   }
-  if (tc) BVG_TRY(tdnn_umma(w.M, w.XL, kEM * Tm, Tm, 1, P->e_mfa.conv, P->e_mfa.bn_scale, P->e_mfa.bn_shift, 1, 0, nullptr, Bm, Tm, w, st));
+  if (tc) BVG_TRY(tdnn_umma(w.M, &Mc, XLc, P->e_mfa.conv, P->e_mfa.bn_scale, P->e_mfa.bn_shift, 1, 0, nullptr, Bm, Tm, st));
   else BVG_TRY(tdnn_f32(w.M, kEM * Tm, w.XL, nullptr, kEM * Tm, Tm, 1, P->e_mfa, Bm, Tm, st));
   // AttentiveStatisticsPooling :282-338.  The tdnn over cat([x, mean, std]) splits into a conv over x
   // plus a per-utterance term from (mean, std).
@@ -379,9 +410,9 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
   ConvEpilogue ec;
   BVG_TRY(conv_f32(w.actx, kEA, w.ms, nullptr, 2 * kEM, 1, 1, P->e_asp_ctx, ec, Bm, 1, 1, 0, st));
   if (tc) {
-    BVG_TRY(tdnn_umma(w.A1, w.M, kEM * Tm, Tm, 1, P->e_asp_tdnn.conv, P->e_asp_tdnn.bn_scale, P->e_asp_tdnn.bn_shift, 1,
-                      /*tanh*/ 1, w.actx, Bm, Tm, w, st));
-    BVG_TRY(tdnn_umma(w.A2, w.A1, kEA * Tm, Tm, 1, P->e_asp_conv, nullptr, nullptr, 0, 0, nullptr, Bm, Tm, w, st));
+    BVG_TRY(tdnn_umma(nullptr, &A1c, Mc, P->e_asp_tdnn.conv, P->e_asp_tdnn.bn_scale, P->e_asp_tdnn.bn_shift, 1,
+                      /*tanh*/ 1, w.actx, Bm, Tm, st));
+    BVG_TRY(tdnn_umma(w.A2, nullptr, A1c, P->e_asp_conv, nullptr, nullptr, 0, 0, nullptr, Bm, Tm, st));
   } else {
     BVG_TRY(tdnn_f32(w.A1, kEA * Tm, w.M, nullptr, kEM * Tm, Tm, 1, P->e_asp_tdnn, Bm, Tm, st, w.actx, /*tanh*/ 1));
     ConvEpilogue ea;
@@ -1000,11 +1031,24 @@ static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtyp
   }
   // speaker conditioning vectors cond_layer(spk), conds[i](spk)  (models.py:226, :233-234): [Bm, C]
   {
-    ConvEpilogue ep;
-    BVG_TRY(conv_f32(g.cond[0], P->C[0], spk, nullptr, E, 1, 1, P->cond_layer, ep, Bm, 1, 1, 0, st));
+    // all of them read the same [Bm, E] embedding: one launch per kMaxMatvecJobs layers
+    MatvecJob jobs[kMaxMatvecJobs];
+    int nj = 0;
+    auto add = [&](const ConvLayer& L, float* y) -> int {
+      MatvecJob j;
+      j.w = L.w; j.bias = L.bias; j.y = y; j.Cout = L.Cout;
+      jobs[nj++] = j;
+      if (nj == kMaxMatvecJobs) { BVG_TRY(matvec_multi_launch(jobs, nj, spk, Bm, E, st)); nj = 0; }
+      return BVG_OK;
+    };
+    BVG_CHECK_ARG(P->cond_layer.K == 1 && P->cond_layer.Cin == E, "decode: cond_layer is a 1x1 conv of the embedding");
+    BVG_TRY(add(P->cond_layer, g.cond[0]));
     if (c.cond_in_each_up_layer)
-      for (int i = 0; i < P->n_stage; ++i)
-        BVG_TRY(conv_f32(g.cond[i + 1], P->C[i + 1], spk, nullptr, E, 1, 1, P->conds[i], ep, Bm, 1, 1, 0, st));
+      for (int i = 0; i < P->n_stage; ++i) {
+        BVG_CHECK_ARG(P->conds[i].K == 1 && P->conds[i].Cin == E, "decode: conds[%d] is a 1x1 conv of the embedding", i);
+        BVG_TRY(add(P->conds[i], g.cond[i + 1]));
+      }
+    if (nj) BVG_TRY(matvec_multi_launch(jobs, nj, spk, Bm, E, st));
   }
   if (dtype == BVG_BF16 && P->umma)
     return decode_bf16_umma(P, latent_any, latent_dtype, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st, lens);

@@ -17,7 +17,10 @@ struct C8T {
   // length, so each utterance of a ragged batch is computed exactly as if decoded alone.  nullptr: all utterances have T rows.
   const int* lens = nullptr;
   int len_mul = 1;
-  int64_t batch_stride() const { return (int64_t)chunks * Tp * 8; }
+  // elements between utterances; non-zero `bstride` makes this a channel-slice view of a wider tensor (speaker encoder:
+  // the three SERes2Net outputs live side by side in the 1536-channel tensor the MFA layer reads)
+  int64_t bstride = 0;
+  int64_t batch_stride() const { return bstride ? bstride : (int64_t)chunks * Tp * 8; }
 };
 inline C8T make_c8t(void* p, int C, int T) {
   C8T t;
@@ -90,6 +93,11 @@ struct UmmaConvParams {
   int split_hi_chunks;                // split convs: 8-channel chunks of the hi half (taps >= tap_mod have zero weights beyond), else 0
 };
 
+// Res2Net chain of one SERes2NetBlock in one launch (ecapa.cu); *taken = false when the shape does not fit (the caller
+// then runs the seven convs separately).  y2 (fp32 [B,512,T]) and / or yc (c8t bf16) receive all eight groups.
+int res2net_chain_launch(const float* y1, float* y2, const C8T* yc, const float* const* w, const float* const* bias,
+                         const float* const* bn_scale, const float* const* bn_shift, int dil, int64_t B, int64_t T,
+                         bool* taken, cudaStream_t st);
 void umma_choose_nb(int Cout, int nph, int* NB, int* n_nblk);
 int64_t umma_pack_elems(int Cout, int Cin, int K, int nph);
 int umma_pack_launch(__nv_bfloat16* dst, const float* src_torch_layout, int Cout, int Cin, int K, int transposed,

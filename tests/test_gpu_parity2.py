@@ -370,3 +370,19 @@ def test_varlen_short_utterances_and_ragged_api(P):
         ref = m.decode(lat[i:i + 1, :n].contiguous(), mel_ref=mel[:1])
         assert outs[i].shape == ref[0].shape
         assert O.snr_db(ref[0].float().cpu(), outs[i].float().cpu()) >= 40.0, (i, n)
+
+
+# ------------------------------------------------------------------ speaker encoder at real shapes (Res2Net chain kernel)
+@pytest.mark.parametrize("Tm,Bm", [(281, 3), (5, 2), (64, 1), (192, 2), (320, 2), (333, 1), (640, 1), (700, 1), (1500, 1)])
+def test_speaker_encoder_real_shapes_vs_oracle(P, Tm, Bm):
+    """ECAPA_TDNN.forward (ECAPA_TDNN.py:543-581) on the IndexTTS-1.5 encoder: reference-mel lengths around the pass
+    boundaries of csrc/ecapa.cu's cluster kernel (64 x {3,4,5} time lanes, one or two passes), the shortest the reflect
+    padding allows, and lengths that fall back to separate conv launches (> 640 frames)."""
+    m, sd, h = _model(P, "full", 0, "wild")
+    _, mel = O.synthetic_inputs(h, Bm, 8, Tm, seed=Tm)
+    sdc = {k: v.cuda() for k, v in O.fold_weight_norm(sd).items()}
+    with torch.no_grad():
+        ref = O.ecapa_forward(mel.cuda(), sdc).cpu().reshape(Bm, -1)
+    spk = m.speaker_embed(mel.cuda()).cpu().reshape(Bm, -1)
+    assert spk.shape == ref.shape
+    assert float((spk - ref).abs().max()) <= 5e-5 * max(1.0, float(ref.abs().max()))
