@@ -471,7 +471,8 @@ __global__ void pack_umma_kernel(__nv_bfloat16* __restrict__ dst, const float* _
 // plain [B,C,T] (fp32 or bf16) <-> c8t bf16
 template <typename TS>
 __global__ void to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const TS* __restrict__ src, int64_t sb, int64_t sc,
-                              int64_t st_, int C, int chunks, int T, int Tp, int pad, const int* __restrict__ lens, int len_mul) {
+                              int64_t st_, int C, int chunks, int T, int Tp, int pad, const int* __restrict__ lens, int len_mul,
+                              int reflect) {
   // one thread per (b, chunk, row) 16-byte vector, pads and padding channels zeroed
   const int64_t n = (int64_t)gridDim.y * chunks * Tp;
   (void)n;
@@ -479,7 +480,11 @@ __global__ void to_c8t_kernel(__nv_bfloat16* __restrict__ dst, const TS* __restr
   if (lens) T = lens[b] * len_mul;                                  // ragged batch: rows past the utterance's end are zero
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)chunks * Tp; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i / Tp), row = (int)(i % Tp);
-    const int t = row - pad;
+    int t = row - pad;
+    // `reflect` halo rows on each side mirror the signal (speechbrain's "same" reflect padding, nnet/CNN.py:458-488), so
+    // that the zero-padding tcgen05 conv computes the reflect-padded one; all other halo rows are zero
+    if (t < 0 && t >= -reflect) t = -t;
+    else if (t >= T && t < T + reflect) t = 2 * (T - 1) - t;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -701,16 +706,17 @@ int conv_umma_launch(const UmmaLayer& L, const C8T& x, const C8T& y, const UmmaE
 
 
 int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B,
-                  cudaStream_t st) {
+                  cudaStream_t st, int reflect) {
   if (B == 0) return BVG_OK;
+  BVG_CHECK_ARG(reflect >= 0 && reflect <= dst.pad && reflect < dst.T && !(reflect && dst.lens), "to_c8t: bad reflect halo");
   dim3 grid((unsigned)std::min<int64_t>(((int64_t)dst.chunks * dst.Tp + 255) / 256, 4096), (unsigned)B);
   ProfScope prof(st, KC_OTHER);
   if (src_dtype == BVG_F32)
-    to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
+    to_c8t_kernel<float><<<grid, 256, 0, st>>>(dst.p, (const float*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul, reflect);
   else if (src_dtype == BVG_BF16)
-    to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
+    to_c8t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dst.p, (const __nv_bfloat16*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul, reflect);
   else if (src_dtype == BVG_F16)
-    to_c8t_kernel<__half><<<grid, 256, 0, st>>>(dst.p, (const __half*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul);
+    to_c8t_kernel<__half><<<grid, 256, 0, st>>>(dst.p, (const __half*)src, sb, sc, st_, dst.C, dst.chunks, dst.T, dst.Tp, dst.pad, dst.lens, dst.len_mul, reflect);
   else { set_error("to_c8t: unsupported dtype"); return BVG_ERR_INVALID; }
   BVG_LAUNCHED();
   return BVG_OK;

@@ -41,13 +41,24 @@ struct ChainParams {
   const float* bn_shift[7];
   int T, dil, row;                 // row = floats per shared-memory row
   int npass;
+  int staged;                      // shared memory holds a [64][T] staging buffer for the next conv's x_j
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+// cluster barrier without memory ordering: "I have finished READING my input buffer" (the values are consumed)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 
 template <int MP>
 __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P) {
   extern __shared__ __align__(16) float smem_f[];
   float* in = smem_f;                                   // [64][row]: position dil + t holds sample t
-  float* ws = smem_f + (size_t)kCH * P.row;             // [3][64][16]
+  float* ws = smem_f + (size_t)kCH * P.row;             // [2][3][64][16]: this conv's weight slice, the next one's in flight
+  float* stage = ws + 2 * 3 * kCH * kCo;                // [64][T]: x_{j+1} lands here (cp.async) while conv j runs
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -60,31 +71,50 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
   float* rin[kRanks];
 #pragma unroll
   for (int r = 0; r < kRanks; ++r) rin[r] = cluster.map_shared_rank(in, r);
+  const int n4 = kCH * T / 4;                           // float4s of one group (64 * T * 4 bytes: always 16-byte granular)
 
-  // group 0 passes through (this CTA copies its 16 channels); rows are zero beyond the halo so that the strided
-  // time lanes of the last pass read zeros
-  for (int i = tid; i < kCH * row / 4; i += 256) reinterpret_cast<float4*>(in)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int i = tid; i < kCo * T; i += 256) {
-    const int c = rank * kCo + i / T, t = i - (i / T) * T;
-    const float v = __ldg(y1b + (int64_t)c * T + t);
-    if (y2b) y2b[(int64_t)c * T + t] = v;
-    if (ycb) ycb[((int64_t)(c >> 3) * P.yc_tp + P.yc_pad + t) * 8 + (c & 7)] = __float2bfloat16_rn(v);
+  // x_j (64 x T contiguous floats) and conv j's weight slice, asynchronously into shared memory
+  auto prefetch = [&](int j) {
+    if (P.staged) {
+      const float4* xj4 = reinterpret_cast<const float4*>(y1b + (int64_t)j * kCH * T);
+      for (int i = tid; i < n4; i += 256) cp_async16(reinterpret_cast<float4*>(stage) + i, xj4 + i);
+    }
+    const float* wj = P.w[j - 1];
+    float* wd = ws + (j & 1) * (3 * kCH * kCo);
+    for (int i = tid; i < 3 * kCH * (kCo / 4); i += 256) {
+      const int q = i & 3, kc = i >> 2;                 // kc = k * 64 + ci
+      cp_async16(wd + kc * kCo + q * 4, wj + (int64_t)kc * kCH + rank * kCo + q * 4);
+    }
+  };
+  prefetch(1);
+  // rows are zero beyond the halo: the strided time lanes of the last pass read (and discard) those positions
+  for (int i = tid; i < kCH * (row - T); i += 256) { const int c = i / (row - T); in[c * row + T + (i - c * (row - T))] = 0.f; }
+  // group 0 passes through (this CTA copies its 16 channels), eight independent loads at a time
+  for (int i0 = tid; i0 < kCo * T; i0 += 256 * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * 256; v[u] = i < kCo * T ? __ldg(y1b + (int64_t)rank * kCo * T + i) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 256;
+      if (i >= kCo * T) continue;
+      const int c = rank * kCo + i / T, t = i - (i / T) * T;
+      if (y2b) y2b[(int64_t)c * T + t] = v[u];
+      if (ycb) ycb[((int64_t)(c >> 3) * P.yc_tp + P.yc_pad + t) * 8 + (c & 7)] = __float2bfloat16_rn(v[u]);
+    }
   }
-  __syncthreads();
 
   for (int j = 1; j < 8; ++j) {
-    // (a) conv input x_j (+ y_{j-1}, already in the buffer), reflect halo, this CTA's weight slice
-    const float* xj = y1b + (int64_t)j * kCH * T;
+    // (a) conv input x_j (+ y_{j-1}, already in the buffer), reflect halo
+    cp_async_wait_all();
+    __syncthreads();
     {
-      // 64 x T contiguous floats (16-byte aligned: 64 * T * 4 bytes per group); batches of six independent float4 loads
-      // per thread -- one load per loop iteration made this phase a chain of L2 round trips (25 us per conv)
-      const float4* xj4 = reinterpret_cast<const float4*>(xj);
-      const int n4 = kCH * T / 4;
+      const float4* xj4 = P.staged ? reinterpret_cast<const float4*>(stage)
+                                   : reinterpret_cast<const float4*>(y1b + (int64_t)j * kCH * T);
       for (int i0 = tid; i0 < n4; i0 += 256 * 6) {
         float4 v[6];
 #pragma unroll
-        for (int u = 0; u < 6; ++u) { const int i = i0 + u * 256; v[u] = i < n4 ? __ldg(xj4 + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int u = 0; u < 6; ++u) { const int i = i0 + u * 256; v[u] = i < n4 ? xj4[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
           const int i = i0 + u * 256;
@@ -100,12 +130,6 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
         }
       }
     }
-    const float* wj = P.w[j - 1];
-    for (int i = tid; i < 3 * kCH * (kCo / 4); i += 256) {
-      const int q = i & 3, kc = i >> 2;                 // kc = k * 64 + ci
-      *reinterpret_cast<float4*>(ws + kc * kCo + q * 4) =
-          *reinterpret_cast<const float4*>(wj + (int64_t)kc * kCH + rank * kCo + q * 4);
-    }
     __syncthreads();
     for (int i = tid; i < kCH * dil; i += 256) {
       const int c = i / dil, o = 1 + (i - c * dil);
@@ -114,6 +138,8 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
       rp[T - 1 + o] = rp[T - 1 - o];
     }
     __syncthreads();
+    if (j < 7) prefetch(j + 1);                         // lands while this conv computes
+    const float* wsj = ws + (j & 1) * (3 * kCH * kCo);
     const int co = rank * kCo + cgq * 4;                // first of this thread's four output channels
     const float4 bi = *reinterpret_cast<const float4*>(P.bias[j - 1] + co);
     const float4 sc = *reinterpret_cast<const float4*>(P.bn_scale[j - 1] + co);
@@ -132,7 +158,7 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
       for (int ci = 0; ci < kCH; ++ci) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float4 w4 = *reinterpret_cast<const float4*>(ws + (k * kCH + ci) * kCo + cgq * 4);
+          const float4 w4 = *reinterpret_cast<const float4*>(wsj + (k * kCH + ci) * kCo + cgq * 4);
           const float* xr = xin + ci * row + k * dil;
 #pragma unroll
           for (int m = 0; m < MP; ++m) {
@@ -152,8 +178,26 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
         outv[p][3][m] = fmaf(fmaxf(acc[3][m] + bi.w, 0.f), sc.w, sh.w);
       }
     }
-    cluster.sync();                                     // every CTA has finished reading its input buffer
-    // (d) y_j: to global memory and into the input buffers of the whole cluster (the next conv adds x_{j+1})
+    if (j < 7) {
+      cluster_sync_relaxed();                           // every CTA has finished reading its input buffer
+      // (d) y_j into the input buffers of the whole cluster (the next conv adds x_{j+1})
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        if (p >= P.npass) break;
+#pragma unroll
+        for (int m = 0; m < MP; ++m) {
+          const int t = p * (kLanes * MP) + m * kLanes + tt;
+          if (t >= T) continue;
+#pragma unroll
+          for (int r = 0; r < kRanks; ++r) {
+            float* d = rin[r] + co * row + dil + t;
+            d[0] = outv[p][0][m]; d[row] = outv[p][1][m]; d[2 * row] = outv[p][2][m]; d[3 * row] = outv[p][3][m];
+          }
+        }
+      }
+      cluster.sync();                                   // y_j is in place everywhere
+    }
+    // y_j to global memory, after the barrier: a release barrier would otherwise wait for these stores to drain
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       if (p >= P.npass) break;
@@ -173,23 +217,16 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
           pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
           *reinterpret_cast<uint2*>(ycb + ((int64_t)(c >> 3) * P.yc_tp + P.yc_pad + t) * 8 + (c & 7)) = pk;
         }
-        if (j < 7) {
-#pragma unroll
-          for (int r = 0; r < kRanks; ++r) {
-            float* d = rin[r] + co * row + dil + t;
-            d[0] = v0; d[row] = v1; d[2 * row] = v2; d[3 * row] = v3;
-          }
-        }
       }
     }
-    cluster.sync();                                     // y_j is in place everywhere
   }
+  cluster.sync();                                       // no CTA leaves while a peer may still address its shared memory
 }
 
 }  // namespace
 
 // Whether the chain kernel takes this shape (else the caller runs the seven convs as separate launches).
-static bool chain_geometry(int T, int dil, int* mp, int* npass, int* row, size_t* smem) {
+static bool chain_geometry(int T, int dil, int* mp, int* npass, int* row, size_t* smem, int* staged) {
   if (dil < 1 || dil > 8 || T <= dil) return false;
   int best = 0, best_cover = 1 << 30;
   for (int m = 3; m <= 5; ++m) {
@@ -201,23 +238,26 @@ static bool chain_geometry(int T, int dil, int* mp, int* npass, int* row, size_t
   *mp = best;
   *npass = best_cover / (kLanes * best);
   *row = ((best_cover + 2 * dil + 3) / 4) * 4 + 4;
-  *smem = ((size_t)kCH * *row + 3 * kCH * kCo) * sizeof(float);
+  const size_t base = ((size_t)kCH * *row + 2 * 3 * kCH * kCo) * sizeof(float);
+  const size_t with_stage = base + (size_t)kCH * T * sizeof(float);
+  *staged = with_stage <= 227 * 1024;
+  *smem = *staged ? with_stage : base;
   return *smem <= 227 * 1024;
 }
 
 int res2net_chain_launch(const float* y1, float* y2, const C8T* yc, const float* const* w, const float* const* bias,
                          const float* const* bn_scale, const float* const* bn_shift, int dil, int64_t B, int64_t T,
                          bool* taken, cudaStream_t st) {
-  int mp, npass, row;
+  int mp, npass, row, staged;
   size_t smem;
   *taken = false;
-  if (B == 0 || B > 65535 || T > (1 << 20) || !chain_geometry((int)T, dil, &mp, &npass, &row, &smem)) return BVG_OK;
+  if (B == 0 || B > 65535 || T > (1 << 20) || !chain_geometry((int)T, dil, &mp, &npass, &row, &smem, &staged)) return BVG_OK;
   ChainParams P;
   P.y1 = y1; P.y2 = y2;
   P.yc = yc ? yc->p : nullptr; P.yc_tp = yc ? yc->Tp : 0; P.yc_pad = yc ? yc->pad : 0;
   BVG_CHECK_ARG(!yc || (yc->chunks == 8 * kCH / 8 && yc->T == (int)T), "res2net_chain: c8t output geometry");
   for (int j = 0; j < 7; ++j) { P.w[j] = w[j]; P.bias[j] = bias[j]; P.bn_scale[j] = bn_scale[j]; P.bn_shift[j] = bn_shift[j]; }
-  P.T = (int)T; P.dil = dil; P.row = row; P.npass = npass;
+  P.T = (int)T; P.dil = dil; P.row = row; P.npass = npass; P.staged = staged;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kRanks, (unsigned)B);
   cfg.blockDim = dim3(256);

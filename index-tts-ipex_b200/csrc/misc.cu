@@ -114,11 +114,12 @@ struct MatvecJobs {
   int blk0[kMaxMatvecJobs + 1];        // first blockIdx.x of every job
   int njobs;
 };
-// 256 threads = 32 outputs x 8 input slices, sixteen independent loads in flight per thread (one accumulator chain with four
+// 256 (1024) threads = 32 outputs x 8 (32) input slices, sixteen independent loads in flight per thread (one accumulator chain with four
 // loads per round trip made each of these launches ~25 us of L2 latency); several layers that read the same x share a launch.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 matvec_kernel(const MatvecJobs J, const float* __restrict__ x, int Cin) {
-  __shared__ float part[8][32];
+  __shared__ float part[32][32];
+  const int nsl = blockDim.x >> 5;                 // input slices: 8, or 32 for the 3072-input layers of the pooling head
   int j = 0;
   while (j + 1 < J.njobs && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
   const MatvecJob& job = J.job[j];
@@ -130,7 +131,7 @@ matvec_kernel(const MatvecJobs J, const float* __restrict__ x, int Cin) {
   const float* w = job.w;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   if (co < Cout) {
-    const int per = (Cin + 7) / 8;
+    const int per = (Cin + nsl - 1) / nsl;
     const int lo = sl * per, hi = min(Cin, lo + per);
     int ci = lo;
     for (; ci + 16 <= hi; ci += 16) {
@@ -149,8 +150,7 @@ matvec_kernel(const MatvecJobs J, const float* __restrict__ x, int Cin) {
   __syncthreads();
   if (sl == 0 && co < Cout) {
     float v = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v += part[q][threadIdx.x];
+    for (int q = 0; q < nsl; ++q) v += part[q][threadIdx.x];
     if (job.bias) v += job.bias[co];
     if (job.relu) v = fmaxf(v, 0.f);
     if (job.post_scale) v = fmaf(v, job.post_scale[co], job.post_shift[co]);
@@ -211,7 +211,7 @@ int matvec_multi_launch(const MatvecJob* jobs, int njobs, const float* x, int64_
   J.blk0[njobs] = blk;
   dim3 grid((unsigned)blk, (unsigned)B);
   ProfScope prof(st, KC_OTHER);
-  matvec_kernel<<<grid, 256, 0, st>>>(J, x, Cin);
+  matvec_kernel<<<grid, Cin >= 2048 ? 1024 : 256, 0, st>>>(J, x, Cin);
   BVG_LAUNCHED();
   return BVG_OK;
 }

@@ -355,7 +355,8 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
   const int NM = P->cfg.num_mels;
   BVG_CHECK_ARG(Tm >= 5, "speaker encoder: reference mel needs >= 5 frames for reflect padding (got %lld)", (long long)Tm);
   // x.transpose(1,2): read channels-last mel through strides
-  BVG_TRY(tdnn_f32(w.X0, kEC * Tm, mel, nullptr, Tm * NM, 1, NM, P->e_block0, Bm, Tm, st));
+  const bool b0_tc = tc && P->e_block0.conv.wu && BVG_ENV_ONCE("BVG_ECAPA_B0_TC", 1) != 0;
+  if (!b0_tc) BVG_TRY(tdnn_f32(w.X0, kEC * Tm, mel, nullptr, Tm * NM, 1, NM, P->e_block0, Bm, Tm, st));
   const float* X = w.X0;
   int64_t Xsb = kEC * Tm;
   // tensor-core path: activations meet the 1x1 GEMMs as c8t bf16 tensors written by their producers (no fp32 -> c8t ->
@@ -370,7 +371,22 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
     v.bstride = XLc.batch_stride();
     return v;
   };
-  if (tc) BVG_TRY(to_c8t_launch(X0c, w.X0, kEC * Tm, Tm, 1, BVG_F32, Bm, st));
+  if (b0_tc) {
+    // blocks[0] (k = 5 over the mel bins, reflect padding) on the tensor cores as well: the mel goes to c8t bf16 with its
+    // two reflected rows per side in the halo; the output is written in both forms (fp32 residual, c8t GEMM input)
+    const Tdnn& t0 = P->e_block0;
+    const int rp = t0.dil * (t0.conv.K - 1) / 2;
+    C8T melc = make_c8t(w.cx, NM, (int)Tm);
+    BVG_TRY(to_c8t_launch(melc, mel, Tm * NM, 1, NM, BVG_F32, Bm, st, rp));
+    UmmaLayer u;
+    u.w = t0.conv.wu; u.Cin = t0.conv.Cin; u.Cout = t0.conv.Cout; u.K = t0.conv.K; u.dil = t0.dil;
+    UmmaEpilogue ep;
+    ep.bias = t0.conv.bias; ep.relu = 1; ep.post_scale = t0.bn_scale; ep.post_shift = t0.bn_shift; ep.prof_other = 1;
+    ep.yf32 = w.X0;
+    BVG_TRY(conv_umma_launch(u, melc, X0c, ep, Bm, st));
+  } else if (tc) {
+    BVG_TRY(to_c8t_launch(X0c, w.X0, kEC * Tm, Tm, 1, BVG_F32, Bm, st));
+  }
   for (int i = 0; i < 3; ++i) {
     const SERes2& S = P->e_blk[i];
     if (tc) BVG_TRY(tdnn_umma(w.Y1, nullptr, i == 0 ? X0c : xl_slice(i - 1), S.tdnn1.conv, S.tdnn1.bn_scale, S.tdnn1.bn_shift, 1, 0, nullptr, Bm, Tm, st));
@@ -924,7 +940,7 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
   BVG_TRY(upload_key(P, "conv_post.bias", 1, &P->post_bias));
   // speaker encoder
   const std::string S = "speaker_encoder.";
-  BVG_TRY(make_tdnn(P, S + "blocks.0", c.num_mels, kEC, 5, 1, &P->e_block0));
+  BVG_TRY(make_tdnn(P, S + "blocks.0", c.num_mels, kEC, 5, 1, &P->e_block0, 0, -1, um));
   for (int i = 0; i < 3; ++i) {
     const std::string b = S + "blocks." + std::to_string(i + 1);
     SERes2& R = P->e_blk[i];

@@ -118,7 +118,8 @@ int conv_umma_fused_launch(const UmmaLayer& L, const C8T& x, const float* act_al
 size_t actconv_tc_scratch_bytes(int64_t B);
 int actconv_tc_launch(const UmmaLayer& L, const C8T& x, const float* act_alpha, const float* act_beta, const C8T& y,
                       const UmmaEpilogue& ep, int64_t B, void* scratch, cudaStream_t st);
-int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st);
+int to_c8t_launch(const C8T& dst, const void* src, int64_t sb, int64_t sc, int64_t st_, int src_dtype, int64_t B, cudaStream_t st,
+                  int reflect = 0);   // reflect: halo rows on each side that mirror the signal instead of being zero
 int from_c8t_launch(void* dst, const C8T& src, int dst_dtype, int64_t B, cudaStream_t st);
 // Activation1d on c8t tensors (writes the output's zero halo rows / padding channels too)
 // impl: 0 = tensor-core FIRs when the tensor qualifies, else the CUDA-core stencil; 1 = stencil; 2 = tensor cores or error
