@@ -131,42 +131,68 @@ act1d_c8t_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict_
 
 // activation_post output (c8t) -> conv_post (Cin -> 1, K taps, zero pad) -> tanh -> fp32 wav / int16 pcm
 // (models.py:246-248; infer.py:206-212,234 for the pcm epilogue)
+// One thread = four consecutive samples: the 4 + K - 1 input rows of a chunk are loaded once (16 bytes each) and every row
+// feeds up to four outputs; the weights sit in shared memory as [chunk][k][8 channels] so that one (chunk, tap) is two
+// 16-byte loads, and each packed fp32x2 FMA advances the even- and the odd-channel partial sum of an output (the
+// one-sample-per-thread form was instruction bound at 1.3 TB/s: one LDS and two ALU ops per FMA).
+constexpr int kPostMaxK = 7;
 __global__ void __launch_bounds__(256)
 conv_post_c8t_kernel(float* __restrict__ wav, int16_t* __restrict__ pcm, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ w, const float* __restrict__ bias, int Cin, int chunks, int T, int Tp,
                      int pad, int K, int64_t s_lo, int64_t s_hi, const int* __restrict__ lens, int len_mul) {
-  extern __shared__ float wsm[];   // [Cin*K] as [ci][k]
-  for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ __align__(16) float wsm[];   // [nchunk][K][8], zero for channels >= Cin
+  const int nchunk = (Cin + 7) >> 3;
+  for (int i = threadIdx.x; i < nchunk * K * 8; i += blockDim.x) {
+    const int j = i & 7, k = (i >> 3) % K, ch = (i >> 3) / K;
+    const int c = ch * 8 + j;
+    wsm[i] = c < Cin ? w[c * K + k] : 0.f;
+  }
   __syncthreads();
   const int b = blockIdx.y;
   const int64_t Tout = T - s_lo - s_hi;                             // row pitch of the output (longest utterance)
-  const int64_t to = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (to >= Tout) return;
-  if (lens && to + s_lo >= (int64_t)lens[b] * len_mul - s_hi) {     // ragged batch: samples past this utterance's end are zero
-    if (wav) wav[(int64_t)b * Tout + to] = 0.f;
-    if (pcm) pcm[(int64_t)b * Tout + to] = 0;
-    return;
-  }
-  const int64_t t = to + s_lo;
+  const int64_t to0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (to0 >= Tout) return;
+  const int64_t Tb = lens ? (int64_t)lens[b] * len_mul : T;         // ragged batch: samples past this utterance's end are zero
+  const int64_t t0 = to0 + s_lo;
   const int hp = (K - 1) / 2;
-  float acc = bias ? bias[0] : 0.f;
-  const int nchunk = (Cin + 7) >> 3;
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const __nv_bfloat16* xr = x + (((int64_t)b * chunks + ch) * Tp + pad + t - hp) * 8;   // halo rows are zero
-    for (int k = 0; k < K; ++k) {
-      const uint4 v = *reinterpret_cast<const uint4*>(xr + (int64_t)k * 8);
-      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+  const float b0 = bias ? bias[0] : 0.f;
+  f32x2 acc[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = ch * 8 + 2 * j;
-        if (c < Cin) acc = fmaf(wsm[c * K + k], __uint_as_float(wd[j] << 16), acc);
-        if (c + 1 < Cin) acc = fmaf(wsm[(c + 1) * K + k], __uint_as_float(wd[j] & 0xffff0000u), acc);
+  for (int o = 0; o < 4; ++o) acc[o] = pk2(0.f, 0.f);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const __nv_bfloat16* xr = x + (((int64_t)b * chunks + ch) * Tp + pad + t0 - hp) * 8;   // halo rows are zero
+    const float4* wk = reinterpret_cast<const float4*>(wsm + ch * K * 8);
+#pragma unroll
+    for (int r = 0; r < 4 + kPostMaxK - 1; ++r) {
+      if (r >= 4 + K - 1) break;
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + (int64_t)r * 8);
+      const f32x2 x01 = pk2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+      const f32x2 x23 = pk2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+      const f32x2 x45 = pk2(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u));
+      const f32x2 x67 = pk2(__uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int k = r - o;
+        if (k < 0 || k >= K) continue;
+        const float4 wa = wk[2 * k], wb = wk[2 * k + 1];
+        acc[o] = fma2(pk2(wa.x, wa.y), x01, acc[o]);
+        acc[o] = fma2(pk2(wa.z, wa.w), x23, acc[o]);
+        acc[o] = fma2(pk2(wb.x, wb.y), x45, acc[o]);
+        acc[o] = fma2(pk2(wb.z, wb.w), x67, acc[o]);
       }
     }
   }
-  const float yv = tanhf(acc);
-  if (wav) wav[(int64_t)b * Tout + to] = yv;
-  if (pcm) pcm[(int64_t)b * Tout + to] = (int16_t)fminf(fmaxf(32767.f * yv, -32767.f), 32767.f);
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int64_t to = to0 + o;
+    if (to >= Tout) break;
+    float e, od;
+    unpk2(acc[o], e, od);
+    float yv = tanhf((e + od) + b0);
+    if (to + s_lo >= Tb - s_hi) yv = 0.f;
+    if (wav) wav[(int64_t)b * Tout + to] = yv;
+    if (pcm) pcm[(int64_t)b * Tout + to] = (int16_t)fminf(fmaxf(32767.f * yv, -32767.f), 32767.f);
+  }
 }
 
 template <int NCH>
@@ -210,9 +236,10 @@ int conv_post_c8t_launch(float* wav, int16_t* pcm, const C8T& x, const float* w,
   const int64_t Tout = x.T - s_lo - s_hi;
   BVG_CHECK_ARG(Tout >= 0 && s_lo >= 0 && s_hi >= 0, "conv_post: bad crop");
   if (Tout == 0) return BVG_OK;
-  dim3 grid((unsigned)((Tout + 255) / 256), (unsigned)B);
+  BVG_CHECK_ARG(K <= kPostMaxK, "conv_post: at most %d taps", kPostMaxK);
+  dim3 grid((unsigned)((Tout + 1023) / 1024), (unsigned)B);
   ProfScope prof(st, KC_OTHER);
-  conv_post_c8t_kernel<<<grid, 256, (size_t)x.C * K * 4, st>>>(wav, pcm, x.p, w, bias, x.C, x.chunks, x.T, x.Tp, x.pad, K,
+  conv_post_c8t_kernel<<<grid, 256, (size_t)((x.C + 7) / 8) * 8 * K * 4, st>>>(wav, pcm, x.p, w, bias, x.C, x.chunks, x.T, x.Tp, x.pad, K,
                                                               s_lo, s_hi, x.lens, x.len_mul);
   BVG_LAUNCHED();
   return BVG_OK;
