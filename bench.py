@@ -247,6 +247,21 @@ def latency_b1(m, O, h, torch, dev):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
             res[prec] = {"ms": ms, "x_realtime": AUDIO_S_PER_UTT * 1e3 / ms}
+        # the same bf16 decode replayed from a CUDA graph (BigVGAN.make_graphed_decode: the serving form for one utterance,
+        # ~200 launches without their host-side cost)
+        m.precision = "bf16"
+        run = m.make_graphed_decode(1, T0, TM, device=dev)
+        for _ in range(2):
+            run(lat, mel)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            run(lat, mel)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        res["bf16_cuda_graph"] = {"ms": ms, "x_realtime": AUDIO_S_PER_UTT * 1e3 / ms}
     finally:
         m.precision = keep
     return res
