@@ -377,6 +377,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    if args.total_utts:                      # strong scaling (BASELINE config 4: a fixed job of N utterances split over the ranks)
+        assert args.total_utts % world == 0, "--total-utts must divide by the number of GPUs"
+        B = args.total_utts // world
     h = O.indextts15_config()
     sd = O.make_state_dict(h, 0, "tame")
     m = pkg.BigVGAN(h, use_cuda_kernel=True)
@@ -500,7 +503,7 @@ def run_ours(args):
         line = {
             "metric": "bigvgan_decode_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if args.total_utts else "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": workload_config(B, args.precision, world),
             "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -536,6 +539,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default: the benchmark's 32)")
+    ap.add_argument("--total-utts", type=int, default=0, help="strong scaling: total utterances per step, split evenly over the GPUs")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32x3"])
     ap.add_argument("--cpu-frames", type=int, default=200, help="latent frames of the CPU-baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip the B = 1 latencies and the Activation1d sweep")
