@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  const long long dbg_entry = P.dbg ? clock64() : 0;
 
   constexpr uint32_t kXStageBytes = 16u * kTXRows * 16u;          // 20480
   constexpr uint32_t kUpBytes = 6u * 64u * 16u;                   // one of (hi, lo): [kchunk 6][n 64][8] bf16
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     }
     if (P.dbg && lane == 0) {
       long long* d = P.dbg + blockIdx.x * 16;
-      d[0] = dbg_wx; d[1] = dbg_wu; d[4] = clock64() - dbg_start;
+      d[0] = dbg_wx; d[1] = dbg_wu; d[4] = clock64() - dbg_start; d[14] = dbg_start - dbg_entry;
       unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1)); d[13] = (long long)(ns1 - dbg_ns0);
     }
   } else if (warp == kTWIssueDn) {
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(kTThreads, 1) act1d_tc_kernel(const ActTcParam
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (P.dbg && threadIdx.x == kTWStore0 * 32) {
       long long* d = P.dbg + blockIdx.x * 16;
-      d[9] = dbg_ty; d[10] = dbg_tb; d[11] = clock64() - dbg_tstart;
+      d[9] = dbg_ty; d[10] = dbg_tb; d[11] = clock64() - dbg_tstart; d[15] = clock64() - dbg_entry;
     }
   }
   tc_fence_before();

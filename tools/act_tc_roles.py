@@ -9,7 +9,7 @@ import index_tts_ipex_b200 as P  # noqa: E402
 
 L = P.capi.lib()
 names = ["iss_wait_x", "iss_wait_ufree", "iss_wait_afull", "iss_wait_yfree", "iss_total", "snk_wait_ufull", "snk_wait_afree", "-",
-         "snk_total", "sto_wait_yfull", "sto_wait_bar", "sto_total", "-", "iss_ns"]
+         "snk_total", "sto_wait_yfull", "sto_wait_bar", "sto_total", "-", "iss_ns", "prologue", "kernel_total"]
 shapes = [(768, 940, 32), (384, 3760, 32), (192, 15040, 32), (96, 60160, 32), (48, 120320, 32), (24, 240640, 32)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
