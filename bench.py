@@ -262,6 +262,19 @@ def latency_b1(m, O, h, torch, dev):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         res["bf16_cuda_graph"] = {"ms": ms, "x_realtime": AUDIO_S_PER_UTT * 1e3 / ms}
+        # a voice whose embedding is cached (SpeakerEmbeddingCache, the serving case of webui.py:199-221): the decode takes spk
+        spk = m.speaker_embed(mel)
+        for _ in range(2):
+            m.decode(lat, spk=spk)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            m.decode(lat, spk=spk)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res["bf16_cached_voice"] = {"ms": ms, "x_realtime": AUDIO_S_PER_UTT * 1e3 / ms}
     finally:
         m.precision = keep
     return res

@@ -26,9 +26,8 @@ namespace bvg {
 namespace {
 
 constexpr int kCH = 64;            // channels per Res2Net group
-constexpr int kRanks = 4;          // CTAs per cluster
-constexpr int kCo = kCH / kRanks;  // output channels per CTA
-constexpr int kLanes = 64;         // time lanes per CTA (256 threads = 64 lanes x 4 channel quads)
+// RANKS CTAs per cluster (4, or 8 for small batches: twice the SMs per utterance), each owning 64 / RANKS output channels;
+// 256 threads = (64 / RANKS / 4) channel quads x LANES time lanes
 
 struct ChainParams {
   const float* y1;                 // [B, 8*64, T] fp32 (tdnn1 output)
@@ -53,8 +52,9 @@ __device__ __forceinline__ void cluster_sync_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 
-template <int MP>
+template <int MP, int RANKS>
 __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P) {
+  constexpr int kRanks = RANKS, kCo = kCH / RANKS, kNQ = kCo / 4, kLanes = 256 / kNQ;
   extern __shared__ __align__(16) float smem_f[];
   float* in = smem_f;                                   // [64][row]: position dil + t holds sample t
   float* ws = smem_f + (size_t)kCH * P.row;             // [2][3][64][16]: this conv's weight slice, the next one's in flight
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
-  const int cgq = tid & 3, tt = tid >> 2;
+  const int cgq = tid % kNQ, tt = tid / kNQ;
   const int T = P.T, dil = P.dil, row = P.row;
   const float* y1b = P.y1 + (int64_t)b * 8 * kCH * T;
   float* y2b = P.y2 ? P.y2 + (int64_t)b * 8 * kCH * T : nullptr;
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
     }
     const float* wj = P.w[j - 1];
     float* wd = ws + (j & 1) * (3 * kCH * kCo);
-    for (int i = tid; i < 3 * kCH * (kCo / 4); i += 256) {
-      const int q = i & 3, kc = i >> 2;                 // kc = k * 64 + ci
+    for (int i = tid; i < 3 * kCH * kNQ; i += 256) {
+      const int q = i % kNQ, kc = i / kNQ;              // kc = k * 64 + ci
       cp_async16(wd + kc * kCo + q * 4, wj + (int64_t)kc * kCH + rank * kCo + q * 4);
     }
   };
@@ -226,23 +226,42 @@ __global__ void __launch_bounds__(256) res2net_chain_kernel(const ChainParams P)
 }  // namespace
 
 // Whether the chain kernel takes this shape (else the caller runs the seven convs as separate launches).
-static bool chain_geometry(int T, int dil, int* mp, int* npass, int* row, size_t* smem, int* staged) {
+static bool chain_geometry(int T, int dil, int ranks, int* mp, int* npass, int* row, size_t* smem, int* staged) {
   if (dil < 1 || dil > 8 || T <= dil) return false;
+  const int lanes = 256 / (kCH / ranks / 4);
+  const int m_lo = ranks == 8 ? 2 : 3, m_hi = ranks == 8 ? 3 : 5;
   int best = 0, best_cover = 1 << 30;
-  for (int m = 3; m <= 5; ++m) {
-    const int np = (T + kLanes * m - 1) / (kLanes * m);
+  for (int m = m_lo; m <= m_hi; ++m) {
+    const int np = (T + lanes * m - 1) / (lanes * m);
     if (np > 2) continue;
-    if (np * kLanes * m < best_cover) { best_cover = np * kLanes * m; best = m; }
+    if (np * lanes * m < best_cover) { best_cover = np * lanes * m; best = m; }
   }
   if (!best) return false;
   *mp = best;
-  *npass = best_cover / (kLanes * best);
+  *npass = best_cover / (lanes * best);
   *row = ((best_cover + 2 * dil + 3) / 4) * 4 + 4;
-  const size_t base = ((size_t)kCH * *row + 2 * 3 * kCH * kCo) * sizeof(float);
+  const size_t base = ((size_t)kCH * *row + 2 * 3 * kCH * (kCH / ranks)) * sizeof(float);
   const size_t with_stage = base + (size_t)kCH * T * sizeof(float);
   *staged = with_stage <= 227 * 1024;
   *smem = *staged ? with_stage : base;
   return *smem <= 227 * 1024;
+}
+
+template <int MP, int RANKS>
+static int chain_launch_t(const ChainParams& P, int64_t B, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(RANKS, (unsigned)B);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = RANKS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  static std::atomic<uint64_t> opted{0};
+  BVG_TRY(smem_opt_in(res2net_chain_kernel<MP, RANKS>, opted, 227 * 1024));
+  BVG_CUDA(cudaLaunchKernelEx(&cfg, res2net_chain_kernel<MP, RANKS>, P));
+  return BVG_OK;
 }
 
 int res2net_chain_launch(const float* y1, float* y2, const C8T* yc, const float* const* w, const float* const* bias,
@@ -251,33 +270,30 @@ int res2net_chain_launch(const float* y1, float* y2, const C8T* yc, const float*
   int mp, npass, row, staged;
   size_t smem;
   *taken = false;
-  if (B == 0 || B > 65535 || T > (1 << 20) || !chain_geometry((int)T, dil, &mp, &npass, &row, &smem, &staged)) return BVG_OK;
+  if (B == 0 || B > 65535 || T > (1 << 20)) return BVG_OK;
+  int num_sms = 0;
+  BVG_TRY(current_device_sms(&num_sms));
+  // 8-CTA clusters while they all fit on the GPU at once (one utterance: 8 SMs instead of 4), else 4-CTA clusters
+  int ranks = (B * 8 <= num_sms && BVG_ENV_ONCE("BVG_ECAPA_RANKS8", 1)) ? 8 : 4;
+  if (!chain_geometry((int)T, dil, ranks, &mp, &npass, &row, &smem, &staged)) {
+    if (ranks == 4) return BVG_OK;
+    ranks = 4;
+    if (!chain_geometry((int)T, dil, ranks, &mp, &npass, &row, &smem, &staged)) return BVG_OK;
+  }
   ChainParams P;
   P.y1 = y1; P.y2 = y2;
   P.yc = yc ? yc->p : nullptr; P.yc_tp = yc ? yc->Tp : 0; P.yc_pad = yc ? yc->pad : 0;
   BVG_CHECK_ARG(!yc || (yc->chunks == 8 * kCH / 8 && yc->T == (int)T), "res2net_chain: c8t output geometry");
   for (int j = 0; j < 7; ++j) { P.w[j] = w[j]; P.bias[j] = bias[j]; P.bn_scale[j] = bn_scale[j]; P.bn_shift[j] = bn_shift[j]; }
   P.T = (int)T; P.dil = dil; P.row = row; P.npass = npass; P.staged = staged;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kRanks, (unsigned)B);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = kRanks; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr; cfg.numAttrs = 1;
   ProfScope prof(st, KC_OTHER);
-  static std::atomic<uint64_t> opted3{0}, opted4{0}, opted5{0};
-  if (mp == 3) {
-    BVG_TRY(smem_opt_in(res2net_chain_kernel<3>, opted3, 227 * 1024));
-    BVG_CUDA(cudaLaunchKernelEx(&cfg, res2net_chain_kernel<3>, P));
-  } else if (mp == 4) {
-    BVG_TRY(smem_opt_in(res2net_chain_kernel<4>, opted4, 227 * 1024));
-    BVG_CUDA(cudaLaunchKernelEx(&cfg, res2net_chain_kernel<4>, P));
+  if (ranks == 8) {
+    if (mp == 2) BVG_TRY((chain_launch_t<2, 8>(P, B, smem, st)));
+    else BVG_TRY((chain_launch_t<3, 8>(P, B, smem, st)));
   } else {
-    BVG_TRY(smem_opt_in(res2net_chain_kernel<5>, opted5, 227 * 1024));
-    BVG_CUDA(cudaLaunchKernelEx(&cfg, res2net_chain_kernel<5>, P));
+    if (mp == 3) BVG_TRY((chain_launch_t<3, 4>(P, B, smem, st)));
+    else if (mp == 4) BVG_TRY((chain_launch_t<4, 4>(P, B, smem, st)));
+    else BVG_TRY((chain_launch_t<5, 4>(P, B, smem, st)));
   }
   BVG_LAUNCHED();
   *taken = true;

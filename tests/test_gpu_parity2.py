@@ -373,11 +373,13 @@ def test_varlen_short_utterances_and_ragged_api(P):
 
 
 # ------------------------------------------------------------------ speaker encoder at real shapes (Res2Net chain kernel)
-@pytest.mark.parametrize("Tm,Bm", [(281, 3), (5, 2), (64, 1), (192, 2), (320, 2), (333, 1), (640, 1), (700, 1), (1500, 1)])
+@pytest.mark.parametrize("Tm,Bm", [(281, 3), (5, 2), (64, 1), (192, 2), (320, 2), (333, 1), (640, 1), (700, 1), (1500, 1),
+                                   (281, 20), (130, 19), (600, 21)])
 def test_speaker_encoder_real_shapes_vs_oracle(P, Tm, Bm):
     """ECAPA_TDNN.forward (ECAPA_TDNN.py:543-581) on the IndexTTS-1.5 encoder: reference-mel lengths around the pass
     boundaries of csrc/ecapa.cu's cluster kernel (64 x {3,4,5} time lanes, one or two passes), the shortest the reflect
-    padding allows, and lengths that fall back to separate conv launches (> 640 frames)."""
+    padding allows, lengths that fall back to separate conv launches, and batches on either side of the switch from
+    8-CTA to 4-CTA clusters (8 * Bm <= SM count)."""
     m, sd, h = _model(P, "full", 0, "wild")
     _, mel = O.synthetic_inputs(h, Bm, 8, Tm, seed=Tm)
     sdc = {k: v.cuda() for k, v in O.fold_weight_norm(sd).items()}
