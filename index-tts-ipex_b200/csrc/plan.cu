@@ -128,6 +128,12 @@ struct bvg_plan {
   SERes2 e_blk[3];
   ConvLayer e_asp_ctx, e_asp_conv, e_fc;
   float *asp_bn_scale = nullptr, *asp_bn_shift = nullptr;
+  // small batches: the (up to three) AMP blocks of a stage read the same input and only meet in the final sum
+  // (models.py:238-245), so they run on three streams -- one utterance does not fill 148 SMs with one block's kernels
+  cudaStream_t side[2] = {};
+  cudaEvent_t ev_fork = nullptr, ev_chain[3] = {};
+  mutable std::atomic<int> ms_busy{0};   // held while one decode enqueues on the side streams (a second host thread decoding
+                                         // on the same plan at that moment simply stays on its one stream)
 };
 
 namespace {
@@ -443,6 +449,7 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
 struct GenWs {
   void *A, *Y, *T1, *T2, *XS;
   void* edge;               // actconv_tc_launch scratch (exact edge rows of the fused activation)
+  void *Yx[2], *T1x[2], *T2x[2], *edgex[2];   // private buffers of AMP blocks 1 and 2 when they run on their own streams
   void* X3;                 // [hi | lo] c8t staging of one conv input (fp32x3 path)
   float* cond[9];
   float* spk;
@@ -450,6 +457,13 @@ struct GenWs {
   float *latent_dev, *mel_dev, *wav_dev;
   int16_t* pcm_dev;
 };
+
+// AMP blocks of a stage on separate streams: bf16 tensor-core path, at most three blocks, and a problem small enough that
+// one block's kernels leave most SMs idle (BVG_MS_MAX_FRAMES latent frames in the batch, default 1024 = four 10 s utterances)
+bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
+  return dtype == BVG_BF16 && P->umma && P->side[0] && P->cfg.num_kernels >= 2 && P->cfg.num_kernels <= 3 &&
+         B * T0 <= BVG_ENV_ONCE("BVG_MS_MAX_FRAMES", 1024);
+}
 
 void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
   const size_t es = dtype_size(dtype);
@@ -464,6 +478,11 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
   const size_t bytes = (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * es;
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
   g->edge = b.take(actconv_tc_scratch_bytes(B));
+  for (int j = 0; j < 2; ++j) {
+    const bool ms = multi_stream(P, B, T0, dtype);
+    g->Yx[j] = ms ? b.take(bytes) : nullptr; g->T1x[j] = ms ? b.take(bytes) : nullptr; g->T2x[j] = ms ? b.take(bytes) : nullptr;
+    g->edgex[j] = ms ? b.take(actconv_tc_scratch_bytes(B)) : nullptr;
+  }
   g->X3 = nullptr;
   if (dtype == BVG_F32X3) {
     size_t x3 = c8t_bytes(B, 2 * ((P->cfg.gpt_dim + 7) / 8 * 8), T0);
@@ -554,8 +573,10 @@ UmmaLayer ulayer(const ConvLayer& L, int dil, int transposed = 0, int stride = 1
 
 // The bf16 throughput path: c8t activations, tcgen05 convs (models.py:220-248).
 int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, const GenWs& g, int64_t B, int64_t T0, int64_t Bm,
-                     float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st, const int* lens = nullptr) {
+                     float* wav, int16_t* pcm16, int64_t t_lo_pad, int64_t t_hi_pad, cudaStream_t st0, const int* lens = nullptr) {
   const bvg_config& c = P->cfg;
+  const bool ms = multi_stream(P, B, T0, BVG_BF16) && P->ms_busy.exchange(1) == 0;
+  struct Release { const bvg_plan* p; bool on; ~Release() { if (on) p->ms_busy.store(0); } } release{P, ms};
   // ragged batches (bvg_decode_varlen): `lens` = device int32 [B] latent-frame counts; every tensor of a stage carries them
   // with the stage's cumulative upsampling factor, the kernels clip at each utterance's own length (umma.cuh, C8T::lens)
   auto make_c8t = [&](void* p, int C, int T) {
@@ -567,13 +588,13 @@ int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, co
   C8T lat = make_c8t(g.T1, c.gpt_dim, (int)T0);
   // (the GPT hands its latent over in its autocast dtype, gpt/model.py:462-477 under infer.py:194: fp16 / bf16 / fp32 are
   // all ingested directly, [B, T, C] channels-last, no fp32 round trip)
-  BVG_TRY(to_c8t_launch(lat, latent, T0 * c.gpt_dim, 1, c.gpt_dim, latent_dtype, B, st));
+  BVG_TRY(to_c8t_launch(lat, latent, T0 * c.gpt_dim, 1, c.gpt_dim, latent_dtype, B, st0));
   int64_t T = T0;
   C8T xs = make_c8t(g.XS, P->C[0], (int)T);
   {
     UmmaEpilogue ep;
     ep.bias = P->conv_pre.bias; ep.cond = g.cond[0]; ep.cond_B = Bm; ep.zero_pads = 1;
-    BVG_TRY(conv_umma_launch(ulayer(P->conv_pre, 1), lat, xs, ep, B, st));
+    BVG_TRY(conv_umma_launch(ulayer(P->conv_pre, 1), lat, xs, ep, B, st0));
   }
   const float inv_nk = 1.0f / (float)c.num_kernels;
   for (int i = 0; i < P->n_stage; ++i) {
@@ -585,19 +606,27 @@ int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, co
       UmmaEpilogue ep;
       ep.bias = P->ups[i].bias;
       if (c.cond_in_each_up_layer) { ep.cond = g.cond[i + 1]; ep.cond_B = Bm; }
-      BVG_TRY(conv_umma_launch(ulayer(P->ups[i], 1, 1, u), xs, a, ep, B, st));
+      BVG_TRY(conv_umma_launch(ulayer(P->ups[i], 1, 1, u), xs, a, ep, B, st0));
     }
     T = Tn;
-    C8T y = make_c8t(g.Y, ch, (int)T), t1 = make_c8t(g.T1, ch, (int)T), t2 = make_c8t(g.T2, ch, (int)T);
     xs = make_c8t(g.XS, ch, (int)T);
+    if (ms) {                                              // fork: the side streams start once `a` is complete
+      BVG_CUDA(cudaEventRecord(P->ev_fork, st0));
+      for (int j = 1; j < c.num_kernels; ++j) BVG_CUDA(cudaStreamWaitEvent(P->side[j - 1], P->ev_fork, 0));
+    }
     for (int j = 0; j < c.num_kernels; ++j) {
       const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
+      const bool own = ms && j > 0;                        // block j on its own stream with its own temporaries
+      cudaStream_t st = own ? P->side[j - 1] : st0;
+      C8T y = make_c8t(own ? g.Yx[j - 1] : g.Y, ch, (int)T), t1 = make_c8t(own ? g.T1x[j - 1] : g.T1, ch, (int)T),
+          t2 = make_c8t(own ? g.T2x[j - 1] : g.T2, ch, (int)T);
+      void* edge = own ? g.edgex[j - 1] : g.edge;
       const C8T* cur = &a;
       for (int m = 0; m < 3; ++m) {
         // xt = c1(a1(x)): one fused kernel for narrow layers, Activation1d kernel + conv kernel otherwise
         UmmaEpilogue e1;
         e1.bias = R.c1[m].bias;
-        int rc = fused_act_conv(ulayer(R.c1[m], R.dil[m]), *cur, R.alpha[2 * m], R.beta[2 * m], t2, e1, B, g.edge, st);
+        int rc = fused_act_conv(ulayer(R.c1[m], R.dil[m]), *cur, R.alpha[2 * m], R.beta[2 * m], t2, e1, B, edge, st);
         if (rc == BVG_ERR_STATE) {
           BVG_TRY(act1d_c8t_launch(t1, *cur, R.alpha[2 * m], R.beta[2 * m], B, st));
           rc = conv_umma_launch(ulayer(R.c1[m], R.dil[m]), t1, t2, e1, B, st);
@@ -613,8 +642,11 @@ int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, co
           if (j == c.num_kernels - 1) e2.scale = inv_nk;
           e2.zero_pads = 1;
           out = &xs;
+          // the running sum lives in xs: block j's last conv reads what block j - 1's last conv wrote (same order of
+          // additions as on one stream, so the result is bit-identical)
+          if (ms && j > 0) BVG_CUDA(cudaStreamWaitEvent(st, P->ev_chain[j - 1], 0));
         }
-        rc = fused_act_conv(ulayer(R.c2[m], 1), t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], *out, e2, B, g.edge, st);
+        rc = fused_act_conv(ulayer(R.c2[m], 1), t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], *out, e2, B, edge, st);
         if (rc == BVG_ERR_STATE) {
           BVG_TRY(act1d_c8t_launch(t1, t2, R.alpha[2 * m + 1], R.beta[2 * m + 1], B, st));
           rc = conv_umma_launch(ulayer(R.c2[m], 1), t1, *out, e2, B, st);
@@ -622,8 +654,11 @@ int decode_bf16_umma(const bvg_plan* P, const void* latent, int latent_dtype, co
         BVG_TRY(rc);
         if (m < 2) cur = &y;
       }
+      if (ms) BVG_CUDA(cudaEventRecord(P->ev_chain[j], st));
     }
+    if (ms) BVG_CUDA(cudaStreamWaitEvent(st0, P->ev_chain[c.num_kernels - 1], 0));   // join (the chain events are transitive)
   }
+  cudaStream_t st = st0;
   const int chp = P->C[P->n_stage];
   C8T t1 = make_c8t(g.T1, chp, (int)T);
   BVG_TRY(act1d_c8t_launch(t1, xs, P->post_alpha, P->post_beta, B, st));
@@ -885,6 +920,9 @@ int bvg_plan_create(bvg_plan** out, const bvg_config* cfg) {
 void bvg_plan_destroy(bvg_plan* P) {
   if (!P) return;
   cudaSetDevice(P->cfg.device);
+  for (cudaStream_t s : P->side) if (s) cudaStreamDestroy(s);
+  if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  for (cudaEvent_t e : P->ev_chain) if (e) cudaEventDestroy(e);
   for (void* p : P->allocs) cudaFree(p);
   delete P;
 }
@@ -961,6 +999,11 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
   BVG_TRY(make_conv(P, S + "asp.conv.conv.weight", S + "asp.conv.conv.bias", kEM, kEA, 1, false, &P->e_asp_conv, 0, -1, um));
   BVG_TRY(make_bn(P, S + "asp_bn.norm", 2 * kEM, &P->asp_bn_scale, &P->asp_bn_shift));
   BVG_TRY(make_conv(P, S + "fc.conv.weight", S + "fc.conv.bias", E, 2 * kEM, 1, false, &P->e_fc));
+  if (P->umma && BVG_ENV_ONCE("BVG_MULTI_STREAM", 1) != 0) {
+    for (cudaStream_t& s : P->side) BVG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    BVG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    for (cudaEvent_t& e : P->ev_chain) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   BVG_CUDA(cudaDeviceSynchronize());
   P->host.clear();
   P->finalized = true;
