@@ -449,7 +449,7 @@ int ecapa_forward(const bvg_plan* P, const float* mel, int64_t Bm, int64_t Tm, f
 struct GenWs {
   void *A, *Y, *T1, *T2, *XS;
   void* edge;               // actconv_tc_launch scratch (exact edge rows of the fused activation)
-  void *Yx[2], *T1x[2], *T2x[2], *edgex[2];   // private buffers of AMP blocks 1 and 2 when they run on their own streams
+  void *Yx[2], *T1x[2], *T2x[2], *edgex[2], *X3x[2];   // private buffers of AMP blocks 1 and 2 when they run on their own streams
   void* X3;                 // [hi | lo] c8t staging of one conv input (fp32x3 path)
   float* cond[9];
   float* spk;
@@ -458,15 +458,9 @@ struct GenWs {
   int16_t* pcm_dev;
 };
 
-// AMP blocks of a stage on separate streams: bf16 tensor-core path, at most three blocks, and a problem small enough that
-// one block's kernels leave most SMs idle (BVG_MS_MAX_FRAMES latent frames in the batch, default 1024 = four 10 s utterances)
-bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
-  return dtype == BVG_BF16 && P->umma && P->side[0] && P->cfg.num_kernels >= 2 && P->cfg.num_kernels <= 3 &&
-         B * T0 <= BVG_ENV_ONCE("BVG_MS_MAX_FRAMES", 1024);
-}
-
-void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
-  const size_t es = dtype_size(dtype);
+// size of each of the generator's rotating activation buffers: the largest c8t tensor on the bf16 tensor-core path, the
+// largest plain [B, C, T] tensor otherwise
+size_t gen_buf_bytes(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
   int64_t maxel = (int64_t)P->C[0] * T0;
   size_t c8 = std::max(c8t_bytes(B, P->C[0], T0), c8t_bytes(B, P->cfg.gpt_dim, T0));
   int64_t T = T0;
@@ -475,24 +469,47 @@ void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, in
     maxel = std::max<int64_t>(maxel, (int64_t)P->C[i + 1] * T);
     c8 = std::max(c8, c8t_bytes(B, P->C[i + 1], T));
   }
-  const size_t bytes = (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * es;
+  return (dtype == BVG_BF16 && P->umma) ? c8 : (size_t)B * maxel * dtype_size(dtype);
+}
+// [hi | lo] staging buffer of the fp32x3 path
+size_t gen_x3_bytes(const bvg_plan* P, int64_t B, int64_t T0) {
+  size_t x3 = c8t_bytes(B, 2 * ((P->cfg.gpt_dim + 7) / 8 * 8), T0);
+  int64_t Tx = T0;
+  for (int i = 0; i < P->n_stage; ++i) {
+    Tx *= P->cfg.upsample_rates[i];
+    x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i] + 7) / 8 * 8), Tx / P->cfg.upsample_rates[i]));   // ups[i] input
+    x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i + 1] + 7) / 8 * 8), Tx));
+  }
+  return x3;
+}
+
+// AMP blocks of a stage on separate streams (all three precisions), at most three blocks.  Measured (B200, 10 s utterances):
+// B = 1 4.9 -> 3.6 ms, B = 4 +24 %, B = 8 +18 %, B = 16 +11 %, B = 32 +5 % audio-s/s -- while one block's persistent kernel
+// ramps up, drains or leaves SMs idle in its last round of tiles, the other blocks' kernels take the free SMs.  The price is
+// six more rotating buffers; BVG_MS_MAX_EXTRA_GB (default 32) keeps huge batches on one stream, BVG_MS_MAX_FRAMES (latent
+// frames in the batch) and BVG_MULTI_STREAM=0 exist for A/B runs.
+bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
+  if (!(P->side[0] && P->cfg.num_kernels >= 2 && P->cfg.num_kernels <= 3)) return false;
+  if (B * T0 > BVG_ENV_ONCE("BVG_MS_MAX_FRAMES", 1 << 30)) return false;
+  const double extra = 6.0 * (double)gen_buf_bytes(P, B, T0, dtype) + (dtype == BVG_F32X3 ? 2.0 * (double)gen_x3_bytes(P, B, T0) : 0.0);
+  return extra <= (double)BVG_ENV_ONCE("BVG_MS_MAX_EXTRA_GB", 32) * 1073741824.0;
+}
+
+void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
+  const size_t bytes = gen_buf_bytes(P, B, T0, dtype);
+  const bool ms = multi_stream(P, B, T0, dtype);
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
   g->edge = b.take(actconv_tc_scratch_bytes(B));
   for (int j = 0; j < 2; ++j) {
-    const bool ms = multi_stream(P, B, T0, dtype);
     g->Yx[j] = ms ? b.take(bytes) : nullptr; g->T1x[j] = ms ? b.take(bytes) : nullptr; g->T2x[j] = ms ? b.take(bytes) : nullptr;
     g->edgex[j] = ms ? b.take(actconv_tc_scratch_bytes(B)) : nullptr;
+    g->X3x[j] = nullptr;
   }
   g->X3 = nullptr;
   if (dtype == BVG_F32X3) {
-    size_t x3 = c8t_bytes(B, 2 * ((P->cfg.gpt_dim + 7) / 8 * 8), T0);
-    int64_t Tx = T0;
-    for (int i = 0; i < P->n_stage; ++i) {
-      Tx *= P->cfg.upsample_rates[i];
-      x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i] + 7) / 8 * 8), Tx / P->cfg.upsample_rates[i]));   // ups[i] input
-      x3 = std::max(x3, c8t_bytes(B, 2 * ((P->C[i + 1] + 7) / 8 * 8), Tx));
-    }
+    const size_t x3 = gen_x3_bytes(P, B, T0);
     g->X3 = b.take(x3);
+    if (ms) for (int j = 0; j < 2; ++j) g->X3x[j] = b.take(x3);
   }
   for (int i = 0; i <= P->n_stage; ++i) g->cond[i] = b.takef(Bm * P->C[i]);
   g->spk = b.takef(Bm * P->cfg.speaker_embedding_dim);
@@ -999,8 +1016,13 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
   BVG_TRY(make_conv(P, S + "asp.conv.conv.weight", S + "asp.conv.conv.bias", kEM, kEA, 1, false, &P->e_asp_conv, 0, -1, um));
   BVG_TRY(make_bn(P, S + "asp_bn.norm", 2 * kEM, &P->asp_bn_scale, &P->asp_bn_shift));
   BVG_TRY(make_conv(P, S + "fc.conv.weight", S + "fc.conv.bias", E, 2 * kEM, 1, false, &P->e_fc));
-  if (P->umma && BVG_ENV_ONCE("BVG_MULTI_STREAM", 1) != 0) {
-    for (cudaStream_t& s : P->side) BVG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  if (BVG_ENV_ONCE("BVG_MULTI_STREAM", 1) != 0) {
+    // the later blocks have the larger kernels (k = 7, 11 against 3): BVG_MS_PRIO=1 gives their streams scheduling priority
+    int prio_lo = 0, prio_hi = 0;
+    BVG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const int use_prio = BVG_ENV_ONCE("BVG_MS_PRIO", 0);
+    for (int j = 0; j < 2; ++j)
+      BVG_CUDA(cudaStreamCreateWithPriority(&P->side[j], cudaStreamNonBlocking, use_prio ? std::max(prio_hi, prio_lo - 1 - j) : prio_lo));
     BVG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
     for (cudaEvent_t& e : P->ev_chain) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
@@ -1119,7 +1141,11 @@ static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtyp
   }
   // BVG_F32X3: the fp32 path below with the Conv1d layers on the tensor cores (3-term bf16 split); everything else
   // (Activation1d with libdevice sinf, ConvTranspose1d, speaker encoder, conv_post) is the fp32 CUDA-core code
+  void* const x3_main = g.X3;
   void* x3 = g.X3;
+  cudaStream_t const st0 = st;
+  const bool ms = multi_stream(P, B, T0, dtype) && P->ms_busy.exchange(1) == 0;
+  struct Release { const bvg_plan* p; bool on; ~Release() { if (on) p->ms_busy.store(0); } } release{P, ms};
   static const bool x3_precise = [] { const char* e = getenv("BVG_X3_PRECISE_ACT"); return e && e[0] == '1'; }();
   const bool fast_act = dtype == BVG_F32X3 && !x3_precise;
   if (dtype == BVG_F32X3) dtype = BVG_F32;
@@ -1157,8 +1183,18 @@ static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtyp
       }
     }
     T *= u;
+    if (ms) {                                     // fork: the AMP blocks of the stage on three streams (see decode_bf16_umma)
+      BVG_CUDA(cudaEventRecord(P->ev_fork, st0));
+      for (int j = 1; j < c.num_kernels; ++j) BVG_CUDA(cudaStreamWaitEvent(P->side[j - 1], P->ev_fork, 0));
+    }
     for (int j = 0; j < c.num_kernels; ++j) {
       const ResBlock& R = P->res[(size_t)i * c.num_kernels + j];
+      const bool own = ms && j > 0;
+      st = own ? P->side[j - 1] : st0;
+      x3 = own && x3_main ? g.X3x[j - 1] : x3_main;
+      void* const bT1 = own ? g.T1x[j - 1] : g.T1;
+      void* const bT2 = own ? g.T2x[j - 1] : g.T2;
+      void* const bY = own ? g.Yx[j - 1] : g.Y;
       const void* y = g.A;                       // AMPBlock1.forward models.py:65-74
       for (int m = 0; m < 3; ++m) {
         // act -> conv: one pass through the split tensor on the fp32x3 path when the shape qualifies
@@ -1168,23 +1204,27 @@ static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtyp
             const int rc = act_conv_x3((float*)dst, (const float*)src, al, be, L, e, B, T, dil, x3, st);
             if (rc != BVG_ERR_STATE) return rc;
           }
-          BVG_TRY(act_launch(g.T1, src, al, be, B, ch, T, dtype, st, fast_act));
-          return gen_conv(dst, g.T1, L, e, B, T, dil, dtype, st, x3);
+          BVG_TRY(act_launch(bT1, src, al, be, B, ch, T, dtype, st, fast_act));
+          return gen_conv(dst, bT1, L, e, B, T, dil, dtype, st, x3);
         };
         ConvEpilogue e1;
-        BVG_TRY(act_conv(g.T2, y, R.alpha[2 * m], R.beta[2 * m], R.c1[m], e1, R.dil[m]));
+        BVG_TRY(act_conv(bT2, y, R.alpha[2 * m], R.beta[2 * m], R.c1[m], e1, R.dil[m]));
         ConvEpilogue e2;
         e2.res1 = y;                              // x = xt + x
         if (m < 2) {
-          BVG_TRY(act_conv(g.Y, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
-          y = g.Y;
+          BVG_TRY(act_conv(bY, bT2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
+          y = bY;
         } else {                                  // xs += block(x); x = xs / num_kernels (models.py:237-243)
           if (j > 0) e2.res2 = g.XS;
           if (j == c.num_kernels - 1) e2.scale = inv_nk;
-          BVG_TRY(act_conv(g.XS, g.T2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
+          if (ms && j > 0) BVG_CUDA(cudaStreamWaitEvent(st, P->ev_chain[j - 1], 0));   // the running sum in XS, in block order
+          BVG_TRY(act_conv(g.XS, bT2, R.alpha[2 * m + 1], R.beta[2 * m + 1], R.c2[m], e2, 1));
         }
       }
+      if (ms) BVG_CUDA(cudaEventRecord(P->ev_chain[j], st));
     }
+    st = st0; x3 = x3_main;
+    if (ms) BVG_CUDA(cudaStreamWaitEvent(st0, P->ev_chain[c.num_kernels - 1], 0));   // join
   }
   const int chp = P->C[P->n_stage];
   BVG_TRY(act_launch(g.T1, g.XS, P->post_alpha, P->post_beta, B, chp, T, dtype, st, fast_act));
