@@ -462,12 +462,19 @@ def run_ours(args):
     d2h = out_h.numel() * out_h.element_size()
 
     # ---- per-kernel-class device time inside one more step (CUDA events on the launch stream)
+    # (the AMP blocks of a stage normally run on three streams; for this pass they stay on one, so that the events around a
+    # launch time that kernel alone -- the per-class sums therefore exceed ms_per_step, where the kernels overlap)
     barrier()
-    pkg.capi.profile_begin()
-    n_prof = 2
-    for _ in range(n_prof):
+    pkg.capi.lib().bvg_debug_set_multi_stream(0)
+    try:
         m.decode(lat, mel_ref=mel, pcm16=True)
-    prof = pkg.capi.profile_end()
+        pkg.capi.profile_begin()
+        n_prof = 2
+        for _ in range(n_prof):
+            m.decode(lat, mel_ref=mel, pcm16=True)
+        prof = pkg.capi.profile_end()
+    finally:
+        pkg.capi.lib().bvg_debug_set_multi_stream(1)
     if rank == 0:
         es = 2 if args.precision == "bf16" else 4
         fused_on = args.precision == "bf16" and os.environ.get("BVG_FUSE", "1") != "0"
@@ -525,6 +532,9 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "kernel_classes_ms_per_step": {k: {"ms": v[0], "launches": v[1]} for k, v in per_step.items()},
+            "kernel_classes_note": "CUDA events around every launch of one extra step with the three AMP blocks of a stage "
+                                   "serialised on one stream (each kernel timed alone); in the timed steps the blocks run on "
+                                   "three streams and overlap, so ms_per_step is below the sum of the classes",
             "roofline_actconv": {"bound": "hbm", "achieved": fus_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                  "frac": fus_gbs / pk["hbm"], "bytes_per_step": work["fused_bytes"],
                                  "flops_per_step": work["fused_flops"], "launches_per_step": fus_n},

@@ -127,6 +127,10 @@ BVG_API void bvg_debug_set_umma_counters(long long* dev_buf);
  * tensor-core FIR kernels.  Default 10 (env BVG_TC_MIN_MELEMS); 0 = tensor cores whenever the shape qualifies; < 0 restores
  * the default.  Process-wide. */
 BVG_API void bvg_debug_set_tc_min_melems(int melems);
+/* Measurement hook: 0 keeps the AMP blocks of a stage (models.py:238-245) on the caller's stream instead of spreading them
+ * over three streams, so that CUDA events around a launch time that kernel alone (bench.py's per-class pass); 1 restores the
+ * default.  A workspace sized while this is 1 serves both settings. */
+BVG_API void bvg_debug_set_multi_stream(int on);
 /* Activation1d(src) -> Conv1d (+bias, +res1, *scale) in ONE kernel (narrow layers, Cout <= 128): the form the
  * bf16 decode path uses for AMPBlock1's act->conv pairs (models.py:65-74).  Plain [B,C,T] bf16 in/out; status 3
  * when the shape does not qualify.  Test entry point (allocates temporaries). */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "bvg_act1d_c8t_impl_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
     "bvg_debug_set_umma_counters": (None, [_vp]),
     "bvg_debug_set_tc_min_melems": (None, [_int]),
+    "bvg_debug_set_multi_stream": (None, [_int]),
     "bvg_actconv_umma_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "bvg_actconv_impl_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
     "bvg_mel_frames": (_i64, [_i64, _int]),

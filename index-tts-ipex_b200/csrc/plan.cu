@@ -488,8 +488,10 @@ size_t gen_x3_bytes(const bvg_plan* P, int64_t B, int64_t T0) {
 // ramps up, drains or leaves SMs idle in its last round of tiles, the other blocks' kernels take the free SMs.  The price is
 // six more rotating buffers; BVG_MS_MAX_EXTRA_GB (default 32) keeps huge batches on one stream, BVG_MS_MAX_FRAMES (latent
 // frames in the batch) and BVG_MULTI_STREAM=0 exist for A/B runs.
-bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
+std::atomic<int> g_ms_enable{1};     // bvg_debug_set_multi_stream
+bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype, bool for_workspace = false) {
   if (!(P->side[0] && P->cfg.num_kernels >= 2 && P->cfg.num_kernels <= 3)) return false;
+  if (!for_workspace && !g_ms_enable.load()) return false;     // (workspaces are always sized for the multi-stream form)
   if (B * T0 > BVG_ENV_ONCE("BVG_MS_MAX_FRAMES", 1 << 30)) return false;
   const double extra = 6.0 * (double)gen_buf_bytes(P, B, T0, dtype) + (dtype == BVG_F32X3 ? 2.0 * (double)gen_x3_bytes(P, B, T0) : 0.0);
   return extra <= (double)BVG_ENV_ONCE("BVG_MS_MAX_EXTRA_GB", 32) * 1073741824.0;
@@ -497,7 +499,7 @@ bool multi_stream(const bvg_plan* P, int64_t B, int64_t T0, int dtype) {
 
 void carve_gen(const bvg_plan* P, Bump& b, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, GenWs* g) {
   const size_t bytes = gen_buf_bytes(P, B, T0, dtype);
-  const bool ms = multi_stream(P, B, T0, dtype);
+  const bool ms = multi_stream(P, B, T0, dtype, /*for_workspace=*/true);
   g->A = b.take(bytes); g->Y = b.take(bytes); g->T1 = b.take(bytes); g->T2 = b.take(bytes); g->XS = b.take(bytes);
   g->edge = b.take(actconv_tc_scratch_bytes(B));
   for (int j = 0; j < 2; ++j) {
@@ -697,6 +699,7 @@ int64_t bvg_launch_count(void) { return g_launches; }
 void bvg_launch_count_reset(void) { g_launches = 0; }
 
 void bvg_debug_set_tc_min_melems(int melems) { bvg::g_tc_min_melems.store(melems < 0 ? -1 : melems); }
+void bvg_debug_set_multi_stream(int on) { g_ms_enable.store(on ? 1 : 0); }
 
 void bvg_profile_begin(void) {
   g_prof_on = true;
