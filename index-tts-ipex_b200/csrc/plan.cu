@@ -132,6 +132,8 @@ struct bvg_plan {
   // (models.py:238-245), so they run on three streams -- one utterance does not fill 148 SMs with one block's kernels
   cudaStream_t side[2] = {};
   cudaEvent_t ev_fork = nullptr, ev_chain[3] = {};
+  cudaEvent_t ev_h2d[2] = {};            // bvg_decode_host: the latent upload runs on side[0] beside the speaker encoder
+  mutable std::atomic<int> h2d_busy{0};
   mutable std::atomic<int> ms_busy{0};   // held while one decode enqueues on the side streams (a second host thread decoding
                                          // on the same plan at that moment simply stays on its one stream)
 };
@@ -943,6 +945,7 @@ void bvg_plan_destroy(bvg_plan* P) {
   for (cudaStream_t s : P->side) if (s) cudaStreamDestroy(s);
   if (P->ev_fork) cudaEventDestroy(P->ev_fork);
   for (cudaEvent_t e : P->ev_chain) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : P->ev_h2d) if (e) cudaEventDestroy(e);
   for (void* p : P->allocs) cudaFree(p);
   delete P;
 }
@@ -1028,6 +1031,7 @@ int bvg_plan_finalize(bvg_plan* P, int enable_bf16_umma) {
       BVG_CUDA(cudaStreamCreateWithPriority(&P->side[j], cudaStreamNonBlocking, use_prio ? std::max(prio_hi, prio_lo - 1 - j) : prio_lo));
     BVG_CUDA(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
     for (cudaEvent_t& e : P->ev_chain) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t& e : P->ev_h2d) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   BVG_CUDA(cudaDeviceSynchronize());
   P->host.clear();
@@ -1065,6 +1069,9 @@ int bvg_decode(const bvg_plan* P, const float* latent, const float* mel, const f
 static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtype, const int* lens, const float* mel,
                       const float* spk_in, int64_t B, int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16,
                       int64_t t_lo_pad, int64_t t_hi_pad, void* workspace, size_t workspace_bytes, void* stream);
+// set by bvg_decode_host around its bvg_decode call: the latent is still being uploaded on another stream; decode_any waits
+// for this event on its own stream right before the first kernel that reads the latent (i.e. after the speaker encoder)
+static thread_local cudaEvent_t tl_latent_ready = nullptr;
 
 int bvg_decode_lat(const bvg_plan* P, const void* latent_any, int latent_dtype, const float* mel, const float* spk_in, int64_t B,
                    int64_t T0, int64_t Bm, int64_t Tm, int dtype, float* wav, int16_t* pcm16, int64_t t_lo_pad,
@@ -1133,6 +1140,10 @@ static int decode_any(const bvg_plan* P, const void* latent_any, int latent_dtyp
         BVG_TRY(add(P->conds[i], g.cond[i + 1]));
       }
     if (nj) BVG_TRY(matvec_multi_launch(jobs, nj, spk, Bm, E, st));
+  }
+  if (tl_latent_ready) {
+    BVG_CUDA(cudaStreamWaitEvent(st, tl_latent_ready, 0));
+    tl_latent_ready = nullptr;
   }
   if (dtype == BVG_BF16 && P->umma)
     return decode_bf16_umma(P, latent_any, latent_dtype, g, B, T0, Bm, wav, pcm16, t_lo_pad, t_hi_pad, st, lens);
@@ -1247,8 +1258,19 @@ int bvg_decode_host(const bvg_plan* P, const float* latent_host, const float* me
   carve_gen(P, bump, B, T0, Bm, Tm, dtype, &g);
   if (bump.overflow) { set_error("decode_host: workspace too small (%zu < %zu)", workspace_bytes, bump.off); return BVG_ERR_WORKSPACE; }
   const int64_t L = T0 * P->total_up;
-  BVG_CUDA(cudaMemcpyAsync(g.latent_dev, latent_host, (size_t)B * T0 * P->cfg.gpt_dim * 4, cudaMemcpyHostToDevice, st));
+  // the (small) reference mel first; the latent (38 MB for 32 x 10 s) goes up on a side stream while the speaker encoder runs
   BVG_CUDA(cudaMemcpyAsync(g.mel_dev, mel_host, (size_t)Bm * Tm * P->cfg.num_mels * 4, cudaMemcpyHostToDevice, st));
+  const bool split = P->side[0] && P->ev_h2d[0] && g_ms_enable.load() && P->h2d_busy.exchange(1) == 0;
+  struct ReleaseH { const bvg_plan* p; bool on; ~ReleaseH() { if (on) p->h2d_busy.store(0); tl_latent_ready = nullptr; } } release_h{P, split};
+  if (split) {
+    BVG_CUDA(cudaEventRecord(P->ev_h2d[0], st));                    // (the staging buffer may still be read by earlier work on st)
+    BVG_CUDA(cudaStreamWaitEvent(P->side[0], P->ev_h2d[0], 0));
+    BVG_CUDA(cudaMemcpyAsync(g.latent_dev, latent_host, (size_t)B * T0 * P->cfg.gpt_dim * 4, cudaMemcpyHostToDevice, P->side[0]));
+    BVG_CUDA(cudaEventRecord(P->ev_h2d[1], P->side[0]));
+    tl_latent_ready = P->ev_h2d[1];
+  } else {
+    BVG_CUDA(cudaMemcpyAsync(g.latent_dev, latent_host, (size_t)B * T0 * P->cfg.gpt_dim * 4, cudaMemcpyHostToDevice, st));
+  }
   BVG_TRY(bvg_decode(P, g.latent_dev, g.mel_dev, nullptr, B, T0, Bm, Tm, dtype, wav_host ? g.wav_dev : nullptr,
                      pcm16_host ? g.pcm_dev : nullptr, 0, 0, workspace, workspace_bytes, stream));
   if (wav_host) BVG_CUDA(cudaMemcpyAsync(wav_host, g.wav_dev, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
