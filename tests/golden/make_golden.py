@@ -120,9 +120,26 @@ def layer_cases():
     return out
 
 
+def ecapa_real_case():
+    """The speaker encoder of the REAL configuration (IndexTTS-1.5: 100 mel bins, C = 512, 1536-channel MFA, 512-d embedding)
+    on a 281-frame (3 s) reference mel, B = 3 -- the shape the benchmark and infer.py:82-93 feed it."""
+    h = O.indextts15_config()
+    sd = O.make_state_dict(h, 0, "wild")
+    m = ref_model(h, sd)
+    _, mel = O.synthetic_inputs(h, 3, 8, 281, seed=281)
+    with torch.no_grad():
+        y = m.speaker_encoder(mel, None)
+    return dict(digest=np.array(O.state_dict_digest(sd)), wseed=np.array(0), mode=np.array("wild"), Bm=np.array(3),
+                Tm=np.array(281), iseed=np.array(281), y=y.numpy())
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "ecapa_real":      # (added in round 2: leaves the other fixtures untouched)
+        np.savez_compressed(os.path.join(HERE, "ecapa_real.npz"), **ecapa_real_case())
+        print("ok")
+        return
     full = full_forward_cases()
     for name, d in full.items():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **d)
@@ -133,6 +150,7 @@ def main():
             flat[f"{k}.{kk}"] = v
     np.savez_compressed(os.path.join(HERE, "act1d_cases.npz"), **flat)
     np.savez_compressed(os.path.join(HERE, "layer_cases.npz"), **layer_cases())
+    np.savez_compressed(os.path.join(HERE, "ecapa_real.npz"), **ecapa_real_case())
     print("ok")
 
 

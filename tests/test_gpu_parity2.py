@@ -388,3 +388,14 @@ def test_speaker_encoder_real_shapes_vs_oracle(P, Tm, Bm):
     spk = m.speaker_embed(mel.cuda()).cpu().reshape(Bm, -1)
     assert spk.shape == ref.shape
     assert float((spk - ref).abs().max()) <= 5e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_speaker_encoder_real_shape_vs_reference_golden(P):
+    """The same shape against the golden made by the reference module itself (tests/golden/ecapa_real.npz)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ecapa_real.npz"))
+    m, sd, h = _model(P, "full", int(g["wseed"]), str(g["mode"]))
+    assert O.state_dict_digest(sd) == str(g["digest"])
+    _, mel = O.synthetic_inputs(h, int(g["Bm"]), 8, int(g["Tm"]), seed=int(g["iseed"]))
+    ref = torch.from_numpy(g["y"]).reshape(int(g["Bm"]), -1)
+    spk = m.speaker_embed(mel.cuda()).cpu().reshape(int(g["Bm"]), -1)
+    assert float((spk - ref).abs().max()) <= 5e-5 * max(1.0, float(ref.abs().max()))

@@ -76,6 +76,20 @@ def test_layers_vs_reference(golden_dir):
     np.testing.assert_allclose(y.numpy(), g["ecapa_y"], rtol=0, atol=2e-5)
 
 
+def test_speaker_encoder_real_shape_vs_reference(golden_dir):
+    """ECAPA_TDNN.forward of the IndexTTS-1.5 configuration on a 281-frame reference mel (the benchmark's shape), golden made
+    by the reference module itself (tests/golden/make_golden.py::ecapa_real_case)."""
+    g = _load(golden_dir, "ecapa_real")
+    h = O.indextts15_config()
+    sd = O.make_state_dict(h, int(g["wseed"]), str(g["mode"]))
+    assert O.state_dict_digest(sd) == str(g["digest"])
+    _, mel = O.synthetic_inputs(h, int(g["Bm"]), 8, int(g["Tm"]), seed=int(g["iseed"]))
+    with torch.no_grad():
+        y = O.ecapa_forward(mel, O.fold_weight_norm(sd))
+    assert y.shape == g["y"].shape
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5 * max(1.0, float(np.abs(g["y"]).max())))
+
+
 @pytest.mark.parametrize("name", ["full15_tame_T12", "full15_wild_T9", "small_wild_T17_bcast", "small_tame_T1"])
 def test_full_forward_vs_reference(golden_dir, name):
     g = _load(golden_dir, name)
